@@ -1,0 +1,1209 @@
+// libfdsr: C-ABI, context, layer plan, weight packing and launch orchestration (see include/fdsr.h).
+// The plan mirrors UNet.__init__/forward of the reference (model/fastdiffsr_modules/unet.py:224-323);
+// each ResnetBlock becomes two conv_gemm_kernel launches, each Down/Upsample one.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fdsr.h"
+#include "aux_kernels.cuh"
+#include "conv_kernel.cuh"
+
+using namespace fdsr;
+
+namespace {
+
+thread_local std::string g_global_error;
+
+struct HTensor {
+  std::string name;
+  int C = 0, level = 0;
+  bool stats = false;
+  size_t off = 0, stats_off = 0;  // byte offsets inside the workspace
+};
+
+struct HTap {
+  int ky, kx, pos;
+};
+struct HChunk {
+  int slot, c0, gn, vc0, parity;  // parity: -1 or pa*2+pb (space-to-depth plane)
+  std::vector<HTap> taps;
+  std::string wname;
+  int wc0;      // first input channel inside the weight tensor
+  int creal;    // real (non-padded) channels in this chunk
+};
+struct HConv {
+  std::string name;
+  int mode = kModeNormal, N = 0, cout = 0, ncg = 8;
+  int nsrc = 0, src[kMaxSrc] = {-1, -1, -1};
+  int gn_C = 0, gn_nsrc = 0;
+  std::string gn_name;
+  std::vector<HChunk> chunks;
+  std::vector<std::string> bias_names;
+  std::string film_name;
+  int resid = -1, out = -1, out_mode = kOutAct, out_c = 0;
+  // device-side resources
+  size_t w_off = 0;      // into weight arena
+  size_t gamma_off = 0;  // into param arena (floats)
+  size_t bias_off = 0;   // into bias arena (floats), [T][N]
+};
+struct HAttn {
+  std::string name;
+  int in = -1, out = -1, C = 0;
+  size_t w1_off = 0, w2_off = 0, w7_off = 0;  // param arena (floats)
+};
+struct HOp {
+  int kind;  // 0 conv, 1 attention gates
+  int idx;
+};
+
+}  // namespace
+
+struct fdsr_ctx {
+  fdsr_config cfg{};
+  int device = 0, num_sms = 0;
+  std::string err;
+  std::vector<HTensor> tensors;
+  std::vector<HConv> convs;
+  std::vector<HAttn> attns;
+  std::vector<HOp> ops;
+  int t_xin = -1, t_last = -1;
+  // weights
+  std::map<std::string, std::vector<float>> host_w;
+  bool weights_loaded = false;
+  uint8_t* d_weights = nullptr;
+  size_t weights_bytes = 0;
+  float* d_params = nullptr;  // gamma/beta, clam/slam weights
+  size_t params_floats = 0;
+  float* d_bias = nullptr;  // per conv [T][N]
+  size_t bias_floats = 0;
+  // schedule
+  int T = 0;
+  std::map<std::string, std::vector<double>> tables;
+  std::vector<PostCoef> post;
+  // workspace
+  int B = 0, H = 0, W = 0;
+  uint8_t* d_ws = nullptr;
+  size_t ws_bytes = 0;
+  size_t stats_off = 0, stats_bytes = 0;
+  size_t off_cond = 0, off_x = 0, off_eps = 0, off_sr = 0, off_psum = 0, off_pmax = 0, off_gate = 0,
+         off_sp = 0, off_seed = 0;
+  ConvLayer* d_layers = nullptr;
+  bool layers_dirty = true;
+  // bicubic tables (cached per size pair)
+  struct BicTab {
+    int in, out, ksize;
+    int *d_min, *d_cnt, *d_taps;
+  };
+  std::vector<BicTab> bic;
+  uint8_t* d_bic_tmp = nullptr;
+  size_t bic_tmp_bytes = 0;
+  // pinned staging for the host-buffer path
+  uint8_t* h_pin = nullptr;
+  size_t h_pin_bytes = 0;
+  uint8_t* d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+  // graph cache
+  bool use_graph = true;
+  cudaGraphExec_t graph = nullptr;
+  struct {
+    int B = 0, H = 0, W = 0;
+    const void* noise = nullptr;
+    void* trace = nullptr;
+  } gkey;
+  int64_t launches = 0;
+  double flops_per_px = 0.0;  // conv FLOPs per full-resolution output pixel per image
+};
+
+namespace {
+
+int fail(fdsr_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_global_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(c, expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(c, FDSR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                 \
+  } while (0)
+
+int pad_n(int cout) { return cout <= 16 ? 16 : (cout <= 64 ? 64 : (cout <= 128 ? 128 : 256)); }
+
+int add_tensor(fdsr_ctx* c, const std::string& name, int C, int level, bool stats) {
+  HTensor t;
+  t.name = name;
+  t.C = C;
+  t.level = level;
+  t.stats = stats;
+  c->tensors.push_back(t);
+  return int(c->tensors.size()) - 1;
+}
+
+std::vector<HTap> taps3x3() {
+  std::vector<HTap> v;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) v.push_back({ky, kx, ky * kPatchW + kx});
+  return v;
+}
+
+// ResnetBlock (unet.py:104-120) -> two fused conv launches. Returns the output tensor id.
+int add_res(fdsr_ctx* c, const std::string& name, const std::vector<int>& srcs, int cout, int level,
+            const std::string& out_name) {
+  const std::string p = "denoise_fn." + name + ".res_block";
+  int cin = 0;
+  for (int s : srcs) cin += c->tensors[s].C;
+  const int th = add_tensor(c, name + ".h", cout, level, true);
+  const int to = add_tensor(c, out_name, cout, level, true);
+  {
+    HConv k;
+    k.name = name + ".block1";
+    k.N = pad_n(cout);
+    k.cout = cout;
+    k.nsrc = int(srcs.size());
+    for (size_t i = 0; i < srcs.size(); ++i) k.src[i] = srcs[i];
+    k.gn_C = cin;
+    k.gn_nsrc = int(srcs.size());
+    k.gn_name = p + ".block1.block.0";
+    int vc = 0;
+    for (size_t si = 0; si < srcs.size(); ++si)
+      for (int c0 = 0; c0 < c->tensors[srcs[si]].C; c0 += 64, vc += 64)
+        k.chunks.push_back({int(si), c0, 1, vc, -1, taps3x3(), p + ".block1.block.3.weight", vc, 64});
+    k.bias_names = {p + ".block1.block.3.bias"};
+    k.film_name = p + ".noise_func.noise_func.0";
+    k.out = th;
+    c->convs.push_back(k);
+    c->ops.push_back({0, int(c->convs.size()) - 1});
+  }
+  {
+    HConv k;
+    k.name = name + ".block2";
+    k.N = pad_n(cout);
+    k.cout = cout;
+    k.src[0] = th;
+    k.nsrc = 1;
+    k.gn_C = cout;
+    k.gn_nsrc = 1;
+    k.gn_name = p + ".block2.block.0";
+    for (int c0 = 0; c0 < cout; c0 += 64)
+      k.chunks.push_back({0, c0, 1, c0, -1, taps3x3(), p + ".block2.block.3.weight", c0, 64});
+    k.bias_names = {p + ".block2.block.3.bias"};
+    if (cin != cout) {
+      int vc = 0;
+      for (size_t si = 0; si < srcs.size(); ++si) {
+        k.src[k.nsrc] = srcs[si];
+        for (int c0 = 0; c0 < c->tensors[srcs[si]].C; c0 += 64, vc += 64)
+          k.chunks.push_back({k.nsrc, c0, 0, 0, -1, {{0, 0, kPatchW + 1}}, p + ".res_conv.weight", vc, 64});
+        ++k.nsrc;
+      }
+      k.bias_names.push_back(p + ".res_conv.bias");
+    } else {
+      k.resid = srcs[0];
+    }
+    k.out = to;
+    c->convs.push_back(k);
+    c->ops.push_back({0, int(c->convs.size()) - 1});
+  }
+  return to;
+}
+
+int build_plan(fdsr_ctx* c) {
+  const fdsr_config& g = c->cfg;
+  const int inner = g.inner_channel;
+  if (g.in_channel != 6 || g.out_channel != 3)
+    return fail(c, FDSR_E_INVALID, "only in_channel=6 / out_channel=3 (conditional SR) is supported");
+  if (inner % 64 != 0) return fail(c, FDSR_E_INVALID, "inner_channel must be a multiple of 64");
+  if (g.norm_groups != 32) return fail(c, FDSR_E_INVALID, "norm_groups must be 32");
+  if (g.n_levels < 1 || g.n_levels > FDSR_MAX_LEVELS) return fail(c, FDSR_E_INVALID, "bad n_levels");
+  for (int i = 0; i < g.n_levels; ++i)
+    if (g.channel_mults[i] < 1 || inner * g.channel_mults[i] > 256)
+      return fail(c, FDSR_E_INVALID, "channel width %d unsupported (max 256 output channels)",
+                  inner * g.channel_mults[i]);
+  c->t_xin = add_tensor(c, "xin", 16, 0, false);
+  int level = 0, pre = inner, idx = 1;
+  int cur = add_tensor(c, "downs.0", inner, 0, true);
+  {
+    HConv k;
+    k.name = "downs.0";
+    k.N = pad_n(inner);
+    k.cout = inner;
+    k.ncg = 2;
+    k.nsrc = 1;
+    k.src[0] = c->t_xin;
+    k.chunks.push_back({0, 0, 0, 0, -1, taps3x3(), "denoise_fn.downs.0.weight", 0, 6});
+    k.bias_names = {"denoise_fn.downs.0.bias"};
+    k.out = cur;
+    c->convs.push_back(k);
+    c->ops.push_back({0, 0});
+  }
+  std::vector<int> feats{cur};
+  for (int li = 0; li < g.n_levels; ++li) {
+    const int cm = inner * g.channel_mults[li];
+    for (int r = 0; r < g.res_blocks; ++r, ++idx) {
+      const std::string nm = "downs." + std::to_string(idx);
+      cur = add_res(c, nm, {cur}, cm, level, nm);
+      feats.push_back(cur);
+      pre = cm;
+    }
+    if (li != g.n_levels - 1) {
+      const std::string nm = "downs." + std::to_string(idx++);
+      const int to = add_tensor(c, nm, pre, level + 1, true);
+      HConv k;
+      k.name = nm;
+      k.mode = kModeS2D;
+      k.N = pad_n(pre);
+      k.cout = pre;
+      k.nsrc = 1;
+      k.src[0] = cur;
+      for (int pa = 0; pa < 2; ++pa)
+        for (int pb = 0; pb < 2; ++pb)
+          for (int c0 = 0; c0 < pre; c0 += 64) {
+            HChunk ch{0, c0, 0, 0, pa * 2 + pb, {}, "denoise_fn." + nm + ".conv.weight", c0, 64};
+            for (int bdy = (pa ? -1 : 0); bdy <= 0; ++bdy)
+              for (int bdx = (pb ? -1 : 0); bdx <= 0; ++bdx)
+                ch.taps.push_back({2 * bdy + pa + 1, 2 * bdx + pb + 1, (bdy + 1) * kPatchW + (bdx + 1)});
+            k.chunks.push_back(ch);
+          }
+      k.bias_names = {"denoise_fn." + nm + ".conv.bias"};
+      k.out = to;
+      c->convs.push_back(k);
+      c->ops.push_back({0, int(c->convs.size()) - 1});
+      cur = to;
+      ++level;
+      feats.push_back(cur);
+    }
+  }
+  // mid: ResnetBlock + CLAM/SLAM, ResnetBlock (unet.py:274-279)
+  {
+    const int tr = add_res(c, "mid.0", {cur}, pre, level, "mid.0.res");
+    HAttn a;
+    a.name = "mid.0";
+    a.in = tr;
+    a.C = pre;
+    a.out = add_tensor(c, "mid.0", pre, level, true);
+    c->attns.push_back(a);
+    c->ops.push_back({1, 0});
+    cur = add_res(c, "mid.1", {a.out}, pre, level, "mid.1");
+  }
+  idx = 0;
+  for (int li = g.n_levels - 1; li >= 0; --li) {
+    const int cm = inner * g.channel_mults[li];
+    for (int r = 0; r < g.res_blocks + 1; ++r, ++idx) {
+      const int skip = feats.back();
+      feats.pop_back();
+      const std::string nm = "ups." + std::to_string(idx);
+      cur = add_res(c, nm, {cur, skip}, cm, level, nm);
+      pre = cm;
+    }
+    if (li >= 1) {
+      const std::string nm = "ups." + std::to_string(idx++);
+      const int to = add_tensor(c, nm, pre, level - 1, true);
+      HConv k;
+      k.name = nm;
+      k.mode = kModeUp2x;
+      k.N = pad_n(pre);
+      k.cout = pre;
+      k.nsrc = 1;
+      k.src[0] = cur;
+      for (int c0 = 0; c0 < pre; c0 += 64)
+        k.chunks.push_back({0, c0, 0, 0, -1, taps3x3(), "denoise_fn." + nm + ".conv.weight", c0, 64});
+      k.bias_names = {"denoise_fn." + nm + ".conv.bias"};
+      k.out = to;
+      c->convs.push_back(k);
+      c->ops.push_back({0, int(c->convs.size()) - 1});
+      cur = to;
+      --level;
+    }
+  }
+  {
+    HConv k;
+    k.name = "final_conv";
+    k.N = 16;
+    k.cout = g.out_channel;
+    k.nsrc = 1;
+    k.src[0] = cur;
+    k.gn_C = pre;
+    k.gn_nsrc = 1;
+    k.gn_name = "denoise_fn.final_conv.block.0";
+    for (int c0 = 0; c0 < pre; c0 += 64)
+      k.chunks.push_back({0, c0, 1, c0, -1, taps3x3(), "denoise_fn.final_conv.block.3.weight", c0, 64});
+    k.bias_names = {"denoise_fn.final_conv.block.3.bias"};
+    k.out_mode = kOutEpsNCHW;
+    k.out_c = g.out_channel;
+    c->convs.push_back(k);
+    c->ops.push_back({0, int(c->convs.size()) - 1});
+  }
+  c->t_last = cur;
+  // sanity + algorithmic FLOPs (2*MAC, padding counted, real channels only)
+  double fl = 0.0;
+  for (const HConv& k : c->convs) {
+    if (int(k.chunks.size()) > kMaxChunks) return fail(c, FDSR_E_INVALID, "layer %s: too many chunks", k.name.c_str());
+    if (k.gn_C > kMaxGnC) return fail(c, FDSR_E_INVALID, "layer %s: GroupNorm width %d > %d", k.name.c_str(), k.gn_C, kMaxGnC);
+    const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
+    double macs = 0.0;
+    for (const HChunk& ch : k.chunks) macs += double(ch.taps.size()) * ch.creal;
+    fl += 2.0 * macs * k.cout / double(1 << (2 * lvl));
+  }
+  c->flops_per_px = fl;
+  return FDSR_OK;
+}
+
+const std::vector<float>* find_w(fdsr_ctx* c, const std::string& name) {
+  auto it = c->host_w.find(name);
+  return it == c->host_w.end() ? nullptr : &it->second;
+}
+
+template <typename T>
+T to_t(float f);
+template <>
+__half to_t<__half>(float f) { return __float2half_rn(f); }
+template <>
+__nv_bfloat16 to_t<__nv_bfloat16>(float f) { return __float2bfloat16_rn(f); }
+
+template <typename T>
+int pack_weights(fdsr_ctx* c) {
+  // blob layout per (chunk, tap): [channel group][n][8 channels] of T  (K-major, no swizzle)
+  size_t total = 0;
+  for (HConv& k : c->convs) {
+    k.w_off = total;
+    for (const HChunk& ch : k.chunks) total += ch.taps.size() * size_t(k.ncg) * k.N * 16;
+  }
+  std::vector<T> host(total / sizeof(T), to_t<T>(0.f));
+  for (HConv& k : c->convs) {
+    size_t off = k.w_off;
+    for (const HChunk& ch : k.chunks) {
+      const std::vector<float>* w = find_w(c, ch.wname);
+      if (!w) return fail(c, FDSR_E_NOTFOUND, "missing weight %s", ch.wname.c_str());
+      const bool is1x1 = ch.wname.find("res_conv") != std::string::npos;
+      const int kk = is1x1 ? 1 : 3;
+      const size_t cin_w = w->size() / (size_t(k.cout) * kk * kk);
+      for (const HTap& tp : ch.taps) {
+        T* blob = host.data() + off / sizeof(T);
+        for (int cg = 0; cg < k.ncg; ++cg)
+          for (int n = 0; n < k.cout; ++n)
+            for (int j = 0; j < 8; ++j) {
+              const int ci = cg * 8 + j;
+              if (ci >= ch.creal) continue;
+              const size_t wi = ((size_t(n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk +
+                                (is1x1 ? 0 : tp.kx);
+              blob[(size_t(cg) * k.N + n) * 8 + j] = to_t<T>((*w)[wi]);
+            }
+        off += size_t(k.ncg) * k.N * 16;
+      }
+    }
+  }
+  if (c->d_weights) cudaFree(c->d_weights);
+  c->d_weights = nullptr;
+  CUDA_TRY(c, cudaMalloc(&c->d_weights, total));
+  CUDA_TRY(c, cudaMemcpy(c->d_weights, host.data(), total, cudaMemcpyHostToDevice));
+  c->weights_bytes = total;
+  return FDSR_OK;
+}
+
+int upload_params(fdsr_ctx* c) {
+  std::vector<float> p;
+  for (HConv& k : c->convs) {
+    if (k.gn_C == 0) continue;
+    const std::vector<float>*ga = find_w(c, k.gn_name + ".weight"), *be = find_w(c, k.gn_name + ".bias");
+    if (!ga || !be || int(ga->size()) != k.gn_C)
+      return fail(c, FDSR_E_NOTFOUND, "missing/invalid GroupNorm params %s", k.gn_name.c_str());
+    k.gamma_off = p.size();
+    p.insert(p.end(), ga->begin(), ga->end());
+    p.insert(p.end(), be->begin(), be->end());
+  }
+  for (HAttn& a : c->attns) {
+    const std::string q = "denoise_fn." + a.name;
+    const std::vector<float>*w1 = find_w(c, q + ".ca.fc1.weight"), *w2 = find_w(c, q + ".ca.fc2.weight"),
+                            *w7 = find_w(c, q + ".sa.conv1.weight");
+    if (!w1 || !w2 || !w7 || w7->size() != 98) return fail(c, FDSR_E_NOTFOUND, "missing CLAM/SLAM weights of %s", q.c_str());
+    a.w1_off = p.size();
+    p.insert(p.end(), w1->begin(), w1->end());
+    a.w2_off = p.size();
+    p.insert(p.end(), w2->begin(), w2->end());
+    a.w7_off = p.size();
+    p.insert(p.end(), w7->begin(), w7->end());
+  }
+  if (c->d_params) cudaFree(c->d_params);
+  c->d_params = nullptr;
+  CUDA_TRY(c, cudaMalloc(&c->d_params, p.size() * 4 + 16));
+  CUDA_TRY(c, cudaMemcpy(c->d_params, p.data(), p.size() * 4, cudaMemcpyHostToDevice));
+  c->params_floats = p.size();
+  return FDSR_OK;
+}
+
+// y[o] = b[o] + sum_i w[o][i] x[i]   (fp32, like nn.Linear)
+std::vector<float> linear(const std::vector<float>& w, const std::vector<float>& b, const std::vector<float>& x) {
+  const size_t in = x.size(), out = b.size();
+  std::vector<float> y(out);
+  for (size_t o = 0; o < out; ++o) {
+    float a = 0.f;
+    for (size_t i = 0; i < in; ++i) a += w[o * in + i] * x[i];
+    y[o] = a + b[o];
+  }
+  return y;
+}
+
+// Per-step bias tables: conv bias (+ res_conv bias) + FiLM(noise_level_t) (unet.py:22-54, 242-248)
+int build_bias_tables(fdsr_ctx* c) {
+  const int T = c->T, inner = c->cfg.inner_channel;
+  const auto *w1 = find_w(c, "denoise_fn.noise_level_mlp.1.weight"), *b1 = find_w(c, "denoise_fn.noise_level_mlp.1.bias"),
+             *w3 = find_w(c, "denoise_fn.noise_level_mlp.3.weight"), *b3 = find_w(c, "denoise_fn.noise_level_mlp.3.bias");
+  if (!w1 || !b1 || !w3 || !b3) return fail(c, FDSR_E_NOTFOUND, "missing noise_level_mlp weights");
+  const std::vector<double>& nl = c->tables["sqrt_alphas_cumprod_prev"];
+  std::vector<std::vector<float>> temb(T);
+  for (int t = 0; t < T; ++t) {
+    const float level = float(nl[t + 1]);
+    const int count = inner / 2;
+    std::vector<float> enc(inner);
+    for (int i = 0; i < count; ++i) {
+      const float step = float(i) / float(count);
+      const float e = level * expf(-logf(1e4f) * step);
+      enc[i] = sinf(e);
+      enc[count + i] = cosf(e);
+    }
+    std::vector<float> h = linear(*w1, *b1, enc);
+    for (float& v : h) v = v / (1.0f + expf(-v));
+    temb[t] = linear(*w3, *b3, h);
+  }
+  size_t total = 0;
+  for (HConv& k : c->convs) {
+    k.bias_off = total;
+    total += size_t(T) * k.N;
+  }
+  std::vector<float> tab(total, 0.f);
+  for (HConv& k : c->convs) {
+    std::vector<float> base(k.N, 0.f);
+    for (const std::string& bn : k.bias_names) {
+      const auto* b = find_w(c, bn);
+      if (!b || int(b->size()) != k.cout) return fail(c, FDSR_E_NOTFOUND, "missing bias %s", bn.c_str());
+      for (int n = 0; n < k.cout; ++n) base[n] += (*b)[n];
+    }
+    const std::vector<float>*fw = nullptr, *fb = nullptr;
+    if (!k.film_name.empty()) {
+      fw = find_w(c, k.film_name + ".weight");
+      fb = find_w(c, k.film_name + ".bias");
+      if (!fw || !fb) return fail(c, FDSR_E_NOTFOUND, "missing FiLM weights %s", k.film_name.c_str());
+    }
+    for (int t = 0; t < T; ++t) {
+      float* row = tab.data() + k.bias_off + size_t(t) * k.N;
+      for (int n = 0; n < k.N; ++n) row[n] = base[n];
+      if (fw) {
+        const std::vector<float> f = linear(*fw, *fb, temb[t]);
+        for (int n = 0; n < k.cout; ++n) row[n] += f[n];
+      }
+    }
+  }
+  if (c->d_bias) cudaFree(c->d_bias);
+  c->d_bias = nullptr;
+  CUDA_TRY(c, cudaMalloc(&c->d_bias, total * 4 + 16));
+  CUDA_TRY(c, cudaMemcpy(c->d_bias, tab.data(), total * 4, cudaMemcpyHostToDevice));
+  c->bias_floats = total;
+  c->layers_dirty = true;
+  return FDSR_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int upload_layers(fdsr_ctx* c) {
+  const int B = c->B, H = c->H, W = c->W;
+  std::vector<ConvLayer> L(c->convs.size());
+  for (size_t i = 0; i < c->convs.size(); ++i) {
+    const HConv& k = c->convs[i];
+    ConvLayer& l = L[i];
+    memset(&l, 0, sizeof l);
+    const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
+    l.B = B;
+    l.H = H >> lvl;
+    l.W = W >> lvl;
+    l.N = k.N;
+    l.ncg = k.ncg;
+    l.mode = k.mode;
+    for (int s = 0; s < k.nsrc; ++s) {
+      const HTensor& t = c->tensors[k.src[s]];
+      l.src[s].ptr = c->d_ws + t.off;
+      l.src[s].stats = t.stats ? reinterpret_cast<const double*>(c->d_ws + t.stats_off) : nullptr;
+      l.src[s].C = t.C;
+      l.src[s].H = H >> t.level;
+      l.src[s].W = W >> t.level;
+    }
+    l.nchunks = int(k.chunks.size());
+    size_t woff = 0;
+    for (int j = 0; j < l.nchunks; ++j) {
+      const HChunk& ch = k.chunks[j];
+      ConvChunk& d = l.chunk[j];
+      d.src = ch.slot;
+      d.c0 = ch.c0;
+      d.gn = ch.gn;
+      d.vc0 = ch.vc0;
+      d.pix_delta = ch.parity < 0 ? 0 : (ch.parity >> 1) * l.src[ch.slot].W + (ch.parity & 1);
+      d.ntaps = int(ch.taps.size());
+      d.w_off = int(woff);
+      for (int tp = 0; tp < d.ntaps; ++tp) d.tap_pos[tp] = ch.taps[tp].pos;
+      woff += ch.taps.size() * size_t(k.ncg) * k.N * 16;
+    }
+    l.gn_C = k.gn_C;
+    l.gn_nsrc = k.gn_nsrc;
+    l.gn_groups = c->cfg.norm_groups;
+    l.gn_eps = 1e-5f;
+    if (k.gn_C) {
+      l.gamma = c->d_params + k.gamma_off;
+      l.beta = c->d_params + k.gamma_off + k.gn_C;
+    }
+    l.bias = c->d_bias + k.bias_off;
+    l.bias_tstride = k.N;
+    l.resid = k.resid >= 0 ? c->d_ws + c->tensors[k.resid].off : nullptr;
+    l.out_mode = k.out_mode;
+    l.out_c = k.out_c;
+    if (k.out_mode == kOutAct) {
+      const HTensor& t = c->tensors[k.out];
+      l.out = c->d_ws + t.off;
+      l.out_stats = t.stats ? reinterpret_cast<double*>(c->d_ws + t.stats_off) : nullptr;
+    } else {
+      l.out = c->d_ws + c->off_eps;
+    }
+    l.weights = c->d_weights + k.w_off;
+    l.tiles_x = (l.W + kTileW - 1) / kTileW;
+    l.tiles_y = (l.H + kTileH - 1) / kTileH;
+    l.ntiles = B * l.tiles_x * l.tiles_y;
+  }
+  if (!c->d_layers) CUDA_TRY(c, cudaMalloc(&c->d_layers, L.size() * sizeof(ConvLayer)));
+  CUDA_TRY(c, cudaMemcpy(c->d_layers, L.data(), L.size() * sizeof(ConvLayer), cudaMemcpyHostToDevice));
+  c->layers_dirty = false;
+  return FDSR_OK;
+}
+
+template <int N, typename T>
+cudaError_t set_conv_attr() {
+  return cudaFuncSetAttribute(conv_gemm_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              ConvCfg<N>::kSmemBytes);
+}
+template <typename T>
+cudaError_t set_conv_attrs() {
+  cudaError_t e = set_conv_attr<16, T>();
+  if (e == cudaSuccess) e = set_conv_attr<64, T>();
+  if (e == cudaSuccess) e = set_conv_attr<128, T>();
+  if (e == cudaSuccess) e = set_conv_attr<256, T>();
+  return e;
+}
+
+template <int N, typename T>
+int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
+  const int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
+  conv_gemm_kernel<N, T><<<grid, kConvThreads, ConvCfg<N>::kSmemBytes, st>>>(c->d_layers + li, t);
+  CUDA_TRY(c, cudaGetLastError());
+  ++c->launches;
+  return FDSR_OK;
+}
+
+template <typename T>
+int launch_conv(fdsr_ctx* c, int li, int t, cudaStream_t st) {
+  const HConv& k = c->convs[li];
+  const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
+  const int h = c->H >> lvl, w = c->W >> lvl;
+  const int ntiles = c->B * ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH);
+  switch (k.N) {
+    case 16: return launch_conv_t<16, T>(c, li, ntiles, t, st);
+    case 64: return launch_conv_t<64, T>(c, li, ntiles, t, st);
+    case 128: return launch_conv_t<128, T>(c, li, ntiles, t, st);
+    case 256: return launch_conv_t<256, T>(c, li, ntiles, t, st);
+  }
+  return fail(c, FDSR_E_INVALID, "unsupported N=%d", k.N);
+}
+
+template <typename T>
+int launch_attn(fdsr_ctx* c, const HAttn& a, cudaStream_t st) {
+  const HTensor& ti = c->tensors[a.in];
+  const HTensor& to = c->tensors[a.out];
+  const int h = c->H >> ti.level, w = c->W >> ti.level, HW = h * w, C = a.C, R = C / 16;
+  const T* x = reinterpret_cast<const T*>(c->d_ws + ti.off);
+  T* y = reinterpret_cast<T*>(c->d_ws + to.off);
+  float* psum = reinterpret_cast<float*>(c->d_ws + c->off_psum);
+  uint32_t* pmax = reinterpret_cast<uint32_t*>(c->d_ws + c->off_pmax);
+  float* gate = reinterpret_cast<float*>(c->d_ws + c->off_gate);
+  float2* sp = reinterpret_cast<float2*>(c->d_ws + c->off_sp);
+  const int ppb = 32;
+  clam_pool_kernel<T><<<dim3((HW + ppb - 1) / ppb, c->B), 128, 0, st>>>(x, psum, pmax, HW, C, ppb);
+  clam_gate_kernel<<<c->B, 256, (2 * C + 2 * R) * 4, st>>>(psum, pmax, c->d_params + a.w1_off,
+                                                         c->d_params + a.w2_off, gate, HW, C, R);
+  const int64_t nwarp = int64_t(c->B) * HW;
+  slam_pool_kernel<T><<<unsigned((nwarp * 32 + 255) / 256), 256, 0, st>>>(x, gate, sp, c->B, HW, C);
+  slam_apply_kernel<T><<<dim3((HW + 7) / 8, c->B), 256, C * 4, st>>>(
+      x, gate, sp, c->d_params + a.w7_off, y, reinterpret_cast<double*>(c->d_ws + to.stats_off), h, w, C);
+  CUDA_TRY(c, cudaGetLastError());
+  c->launches += 4;
+  return FDSR_OK;
+}
+
+// One UNet evaluation on the context's internal cond / x buffers -> internal eps buffer.
+template <typename T>
+int unet_internal(fdsr_ctx* c, int t, cudaStream_t st) {
+  if (c->layers_dirty) {
+    int rc = upload_layers(c);
+    if (rc) return rc;
+  }
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ws + c->stats_off, 0, c->stats_bytes, st));
+  const int HW = c->H * c->W;
+  const int64_t npix = int64_t(c->B) * HW;
+  pack_input_kernel<T><<<unsigned((npix + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const float*>(c->d_ws + c->off_cond), reinterpret_cast<const float*>(c->d_ws + c->off_x),
+      reinterpret_cast<T*>(c->d_ws + c->tensors[c->t_xin].off), c->B, HW);
+  ++c->launches;
+  for (const HOp& op : c->ops) {
+    int rc = op.kind == 0 ? launch_conv<T>(c, op.idx, t, st) : launch_attn<T>(c, c->attns[op.idx], st);
+    if (rc) return rc;
+  }
+  return FDSR_OK;
+}
+
+int unet_dispatch(fdsr_ctx* c, int t, cudaStream_t st) {
+  return c->cfg.dtype == FDSR_DTYPE_BF16 ? unet_internal<__nv_bfloat16>(c, t, st) : unet_internal<__half>(c, t, st);
+}
+
+int check_ready(fdsr_ctx* c) {
+  if (!c->weights_loaded) return fail(c, FDSR_E_STATE, "fdsr_load_weights has not been called");
+  if (c->T == 0) return fail(c, FDSR_E_STATE, "fdsr_set_schedule has not been called");
+  return FDSR_OK;
+}
+
+int posterior_launch(fdsr_ctx* c, const float* x, const float* eps, const float* z, int t, float* out,
+                     int64_t numel, int use_rng, uint64_t seed, cudaStream_t st) {
+  if (numel % 4) return fail(c, FDSR_E_INVALID, "numel must be a multiple of 4");
+  const int64_t n4 = numel / 4;
+  posterior_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(x, eps, z, out, n4, c->post[t], use_rng, seed,
+                                                             uint32_t(t));
+  CUDA_TRY(c, cudaGetLastError());
+  ++c->launches;
+  return FDSR_OK;
+}
+
+int sample_enqueue(fdsr_ctx* c, const float* noise, uint64_t seed, float* trace, cudaStream_t st) {
+  const int T = c->T, B = c->B;
+  const int64_t per = int64_t(3) * c->H * c->W, numel = per * B;
+  float* x = reinterpret_cast<float*>(c->d_ws + c->off_x);
+  float* cond = reinterpret_cast<float*>(c->d_ws + c->off_cond);
+  float* eps = reinterpret_cast<float*>(c->d_ws + c->off_eps);
+  float* sr = reinterpret_cast<float*>(c->d_ws + c->off_sr);
+  const int nfr = fdsr_trace_frames(c);
+  const unsigned gb = unsigned((numel + 255) / 256);
+  if (noise) {
+    CUDA_TRY(c, cudaMemcpyAsync(x, noise, numel * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    noise_fill_kernel<<<unsigned((numel / 4 + 255) / 256), 256, 0, st>>>(x, numel / 4, seed, uint32_t(T));
+    ++c->launches;
+  }
+  int frame = 0;
+  if (trace) {
+    res2img_kernel<<<gb, 256, 0, st>>>(cond, cond, trace, per, per * nfr, B);
+    ++c->launches;
+    frame = 1;
+  }
+  const int inter = 1 | (T / 10);
+  for (int k = 0, t = T - 1; t >= 0; --t, ++k) {
+    int rc = unet_dispatch(c, t, st);
+    if (rc) return rc;
+    const float* z = (noise && t > 0) ? noise + int64_t(k + 1) * numel : nullptr;
+    rc = posterior_launch(c, x, eps, z, t, x, numel, (!noise && t > 0) ? 1 : 0, seed, st);
+    if (rc) return rc;
+    if (trace && t % inter == 0) {
+      res2img_kernel<<<gb, 256, 0, st>>>(x, cond, trace + per * frame, per, per * nfr, B);
+      ++c->launches;
+      ++frame;
+    }
+  }
+  res2img_kernel<<<gb, 256, 0, st>>>(x, cond, sr, per, per, B);
+  ++c->launches;
+  CUDA_TRY(c, cudaGetLastError());
+  return FDSR_OK;
+}
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for the bicubic filter, full-image box
+int ensure_bic(fdsr_ctx* c, int in, int out) {
+  for (const auto& b : c->bic)
+    if (b.in == in && b.out == out) return FDSR_OK;
+  const double scale = double(in) / out;
+  const double fscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * fscale;
+  const int ksize = int(ceil(support)) * 2 + 1;
+  std::vector<int> vmin(out), vcnt(out), taps(size_t(out) * ksize, 0);
+  std::vector<double> k(ksize);
+  auto filt = [](double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+  };
+  for (int xx = 0; xx < out; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    const double ss = 1.0 / fscale;
+    int xmin = int(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = int(center + support + 0.5);
+    if (xmax > in) xmax = in;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      k[x] = filt((x + xmin - center + 0.5) * ss);
+      ww += k[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) k[x] /= ww;
+      taps[size_t(xx) * ksize + x] =
+          k[x] < 0 ? int(-0.5 + k[x] * (1 << kBicPrec)) : int(0.5 + k[x] * (1 << kBicPrec));
+    }
+    vmin[xx] = xmin;
+    vcnt[xx] = xmax;
+  }
+  fdsr_ctx::BicTab b{in, out, ksize, nullptr, nullptr, nullptr};
+  CUDA_TRY(c, cudaMalloc(&b.d_min, out * 4));
+  CUDA_TRY(c, cudaMalloc(&b.d_cnt, out * 4));
+  CUDA_TRY(c, cudaMalloc(&b.d_taps, taps.size() * 4));
+  CUDA_TRY(c, cudaMemcpy(b.d_min, vmin.data(), out * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(c, cudaMemcpy(b.d_cnt, vcnt.data(), out * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(c, cudaMemcpy(b.d_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
+  c->bic.push_back(b);
+  return FDSR_OK;
+}
+const fdsr_ctx::BicTab* find_bic(const fdsr_ctx* c, int in, int out) {
+  for (const auto& b : c->bic)
+    if (b.in == in && b.out == out) return &b;
+  return nullptr;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* fdsr_global_error(void) { return g_global_error.c_str(); }
+const char* fdsr_last_error(const fdsr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_error.c_str(); }
+
+int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, FDSR_E_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, FDSR_E_CUDA, "no CUDA device: libfdsr has no CPU fallback");
+  fdsr_ctx* c = new fdsr_ctx();
+  c->cfg = *cfg;
+  cudaGetDevice(&c->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess || prop.major != 10) {
+    delete c;
+    return fail(nullptr, FDSR_E_CUDA, "libfdsr needs an sm_100 (B200) device");
+  }
+  c->num_sms = prop.multiProcessorCount;
+  if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
+    delete c;
+    return fail(nullptr, FDSR_E_INVALID, "dtype must be FDSR_DTYPE_FP16 or FDSR_DTYPE_BF16");
+  }
+  const int rc = build_plan(c);
+  if (rc) {
+    g_global_error = c->err;
+    delete c;
+    return rc;
+  }
+  const cudaError_t ae =
+      cfg->dtype == FDSR_DTYPE_BF16 ? set_conv_attrs<__nv_bfloat16>() : set_conv_attrs<__half>();
+  if (ae != cudaSuccess) {
+    delete c;
+    return fail(nullptr, FDSR_E_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ae));
+  }
+  *out = c;
+  return FDSR_OK;
+}
+
+int fdsr_destroy(fdsr_ctx* c) {
+  if (!c) return FDSR_OK;
+  if (c->graph) cudaGraphExecDestroy(c->graph);
+  cudaFree(c->d_weights);
+  cudaFree(c->d_params);
+  cudaFree(c->d_bias);
+  cudaFree(c->d_ws);
+  cudaFree(c->d_layers);
+  cudaFree(c->d_bic_tmp);
+  cudaFree(c->d_stage);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  for (auto& b : c->bic) {
+    cudaFree(b.d_min);
+    cudaFree(b.d_cnt);
+    cudaFree(b.d_taps);
+  }
+  delete c;
+  return FDSR_OK;
+}
+
+int fdsr_load_weights(fdsr_ctx* c, const char* const* names, const float* const* ptrs, const int64_t* numels,
+                      int32_t n) {
+  if (!c || !names || !ptrs || !numels) return fail(c, FDSR_E_INVALID, "null argument");
+  c->host_w.clear();
+  for (int i = 0; i < n; ++i) c->host_w[names[i]] = std::vector<float>(ptrs[i], ptrs[i] + numels[i]);
+  // shape checks against the plan
+  for (const HConv& k : c->convs)
+    for (const HChunk& ch : k.chunks) {
+      const auto* w = find_w(c, ch.wname);
+      if (!w) return fail(c, FDSR_E_NOTFOUND, "state_dict is missing %s", ch.wname.c_str());
+      const bool is1x1 = ch.wname.find("res_conv") != std::string::npos;
+      if (w->size() % (size_t(k.cout) * (is1x1 ? 1 : 9)) != 0)
+        return fail(c, FDSR_E_INVALID, "unexpected size for %s", ch.wname.c_str());
+    }
+  int rc = c->cfg.dtype == FDSR_DTYPE_BF16 ? pack_weights<__nv_bfloat16>(c) : pack_weights<__half>(c);
+  if (rc) return rc;
+  rc = upload_params(c);
+  if (rc) return rc;
+  c->weights_loaded = true;
+  c->layers_dirty = true;
+  if (c->graph) {
+    cudaGraphExecDestroy(c->graph);
+    c->graph = nullptr;
+  }
+  if (c->T) return build_bias_tables(c);
+  return FDSR_OK;
+}
+
+int fdsr_set_schedule(fdsr_ctx* c, const double* betas, int32_t T) {
+  if (!c || !betas || T < 1) return fail(c, FDSR_E_INVALID, "bad schedule");
+  if (!c->weights_loaded) return fail(c, FDSR_E_STATE, "load weights before the schedule (FiLM tables need them)");
+  std::vector<double> b(betas, betas + T), al(T), ac(T), acp(T), pv(T);
+  auto& tb = c->tables;
+  tb.clear();
+  double cp = 1.0;
+  for (int i = 0; i < T; ++i) {
+    al[i] = 1.0 - b[i];
+    acp[i] = cp;
+    cp *= al[i];
+    ac[i] = cp;
+  }
+  std::vector<double> s_ac(T), s_1m(T), l_1m(T), s_r(T), s_rm1(T), plv(T), c1(T), c2(T), nlv(T + 1);
+  nlv[0] = 1.0;
+  for (int i = 0; i < T; ++i) {
+    s_ac[i] = sqrt(ac[i]);
+    s_1m[i] = sqrt(1.0 - ac[i]);
+    l_1m[i] = log(1.0 - ac[i]);
+    s_r[i] = sqrt(1.0 / ac[i]);
+    s_rm1[i] = sqrt(1.0 / ac[i] - 1);
+    pv[i] = b[i] * (1.0 - acp[i]) / (1.0 - ac[i]);
+    plv[i] = log(pv[i] > 1e-20 ? pv[i] : 1e-20);
+    c1[i] = b[i] * sqrt(acp[i]) / (1.0 - ac[i]);
+    c2[i] = (1.0 - acp[i]) * sqrt(al[i]) / (1.0 - ac[i]);
+    nlv[i + 1] = sqrt(ac[i]);
+  }
+  tb["betas"] = b;
+  tb["alphas_cumprod"] = ac;
+  tb["alphas_cumprod_prev"] = acp;
+  tb["sqrt_alphas_cumprod"] = s_ac;
+  tb["sqrt_one_minus_alphas_cumprod"] = s_1m;
+  tb["log_one_minus_alphas_cumprod"] = l_1m;
+  tb["sqrt_recip_alphas_cumprod"] = s_r;
+  tb["sqrt_recipm1_alphas_cumprod"] = s_rm1;
+  tb["posterior_variance"] = pv;
+  tb["posterior_log_variance_clipped"] = plv;
+  tb["posterior_mean_coef1"] = c1;
+  tb["posterior_mean_coef2"] = c2;
+  tb["sqrt_alphas_cumprod_prev"] = nlv;
+  c->T = T;
+  c->post.resize(T);
+  for (int i = 0; i < T; ++i)
+    c->post[i] = PostCoef{float(s_r[i]), float(s_rm1[i]), float(c1[i]), float(c2[i]), expf(0.5f * float(plv[i]))};
+  if (c->graph) {
+    cudaGraphExecDestroy(c->graph);
+    c->graph = nullptr;
+  }
+  return build_bias_tables(c);
+}
+
+int fdsr_get_table(fdsr_ctx* c, const char* name, double* out, int32_t cap) {
+  if (!c || !name || !out) return fail(c, FDSR_E_INVALID, "null argument");
+  auto it = c->tables.find(name);
+  if (it == c->tables.end()) return fail(c, FDSR_E_NOTFOUND, "no table %s", name);
+  if (cap < int(it->second.size())) return fail(c, FDSR_E_INVALID, "capacity too small");
+  memcpy(out, it->second.data(), it->second.size() * 8);
+  return int(it->second.size());
+}
+
+int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
+  if (!c) return FDSR_E_INVALID;
+  const int down = 1 << (c->cfg.n_levels - 1);
+  if (B < 1 || H < down || W < down || H % down || W % down)
+    return fail(c, FDSR_E_INVALID, "B>=1 and H, W multiples of %d required (got %dx%dx%d)", down, B, H, W);
+  if (c->B == B && c->H == H && c->W == W && c->d_ws) return FDSR_OK;
+  size_t off = 0;
+  for (HTensor& t : c->tensors) {
+    t.off = off;
+    off = align_up(off + size_t(B) * (H >> t.level) * (W >> t.level) * t.C * 2, 256);
+  }
+  c->stats_off = off;
+  for (HTensor& t : c->tensors)
+    if (t.stats) {
+      t.stats_off = off;
+      off += size_t(B) * t.C * 8;
+    }
+  // CLAM pools live in the per-forward zeroed region too
+  int cmax = 0, lmin = 99;
+  for (const HAttn& a : c->attns) {
+    cmax = a.C > cmax ? a.C : cmax;
+    lmin = c->tensors[a.in].level < lmin ? c->tensors[a.in].level : lmin;
+  }
+  c->off_psum = off;
+  off += size_t(B) * cmax * 4;
+  c->off_pmax = off;
+  off += size_t(B) * cmax * 4;
+  off = align_up(off, 256);
+  c->stats_bytes = off - c->stats_off;
+  c->off_gate = off;
+  off = align_up(off + size_t(B) * cmax * 4, 256);
+  c->off_sp = off;
+  off = align_up(off + (lmin < 99 ? size_t(B) * (H >> lmin) * (W >> lmin) * 8 : 0), 256);
+  const size_t img = align_up(size_t(B) * 3 * H * W * 4, 256);
+  c->off_cond = off;
+  off += img;
+  c->off_x = off;
+  off += img;
+  c->off_eps = off;
+  off += img;
+  c->off_sr = off;
+  off += img;
+  if (c->d_ws) cudaFree(c->d_ws);
+  c->d_ws = nullptr;
+  CUDA_TRY(c, cudaMalloc(&c->d_ws, off));
+  c->ws_bytes = off;
+  c->B = B;
+  c->H = H;
+  c->W = W;
+  c->layers_dirty = true;
+  if (c->graph) {
+    cudaGraphExecDestroy(c->graph);
+    c->graph = nullptr;
+  }
+  return FDSR_OK;
+}
+
+size_t fdsr_workspace_bytes(const fdsr_ctx* c) { return c ? c->ws_bytes : 0; }
+
+int fdsr_unet_forward(fdsr_ctx* c, const float* cond, const float* xt, int32_t t, float* eps_out, int32_t B,
+                      int32_t H, int32_t W, void* stream) {
+  if (!c || !cond || !xt || !eps_out) return fail(c, FDSR_E_INVALID, "null argument");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (t < 0 || t >= c->T) return fail(c, FDSR_E_INVALID, "t out of range");
+  rc = fdsr_reserve(c, B, H, W);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = size_t(B) * 3 * H * W * 4;
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_ws + c->off_cond, cond, bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_ws + c->off_x, xt, bytes, cudaMemcpyDeviceToDevice, st));
+  rc = unet_dispatch(c, t, st);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemcpyAsync(eps_out, c->d_ws + c->off_eps, bytes, cudaMemcpyDeviceToDevice, st));
+  return FDSR_OK;
+}
+
+int fdsr_posterior_step(fdsr_ctx* c, const float* xt, const float* eps, const float* z, int32_t t, float* out,
+                        int64_t numel, void* stream) {
+  if (!c || !xt || !eps || !out) return fail(c, FDSR_E_INVALID, "null argument");
+  if (c->T == 0) return fail(c, FDSR_E_STATE, "fdsr_set_schedule has not been called");
+  if (t < 0 || t >= c->T) return fail(c, FDSR_E_INVALID, "t out of range");
+  return posterior_launch(c, xt, eps, t > 0 ? z : nullptr, t, out, numel, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int32_t fdsr_trace_frames(const fdsr_ctx* c) {
+  if (!c || c->T == 0) return 0;
+  const int inter = 1 | (c->T / 10);
+  int n = 1;
+  for (int t = c->T - 1; t >= 0; --t)
+    if (t % inter == 0) ++n;
+  return n;
+}
+
+int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t seed, float* sr_out, float* trace,
+                int32_t B, int32_t H, int32_t W, void* stream) {
+  if (!c || !cond || !sr_out) return fail(c, FDSR_E_INVALID, "null argument");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  rc = fdsr_reserve(c, B, H, W);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = size_t(B) * 3 * H * W * 4;
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_ws + c->off_cond, cond, bytes, cudaMemcpyDeviceToDevice, st));
+  // The Philox seed is a kernel argument, so RNG-mode graphs are keyed on it as well via `noise`
+  // == nullptr + re-capture when the seed changes (cheap next to 20 UNet steps).
+  static thread_local uint64_t last_seed = 0;
+  const bool want_graph = c->use_graph;
+  if (want_graph) {
+    if (c->layers_dirty) {
+      rc = upload_layers(c);
+      if (rc) return rc;
+    }
+    const bool hit = c->graph && c->gkey.B == B && c->gkey.H == H && c->gkey.W == W && c->gkey.noise == noise &&
+                     c->gkey.trace == trace && (noise || last_seed == seed);
+    if (!hit) {
+      if (c->graph) {
+        cudaGraphExecDestroy(c->graph);
+        c->graph = nullptr;
+      }
+      cudaStream_t cs;
+      CUDA_TRY(c, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      // make sure every kernel attribute is set before capture (cudaFuncSetAttribute is not capturable)
+      const int64_t l0 = c->launches;
+      CUDA_TRY(c, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      rc = sample_enqueue(c, noise, seed, trace, cs);
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(cs, &g);
+      cudaStreamDestroy(cs);
+      if (rc) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+      if (e != cudaSuccess) return fail(c, FDSR_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&c->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) return fail(c, FDSR_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+      c->gkey.B = B;
+      c->gkey.H = H;
+      c->gkey.W = W;
+      c->gkey.noise = noise;
+      c->gkey.trace = trace;
+      last_seed = seed;
+      c->launches = l0;  // captured, not yet launched
+    }
+    CUDA_TRY(c, cudaGraphLaunch(c->graph, st));
+    // launches per replay: recompute deterministically
+    int per_unet = 1;
+    for (const HOp& op : c->ops) per_unet += op.kind == 0 ? 1 : 4;
+    c->launches += int64_t(c->T) * (per_unet + 1) + 1 + (noise ? 0 : 1) + (trace ? fdsr_trace_frames(c) : 0);
+  } else {
+    rc = sample_enqueue(c, noise, seed, trace, st);
+    if (rc) return rc;
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(sr_out, c->d_ws + c->off_sr, bytes, cudaMemcpyDeviceToDevice, st));
+  return FDSR_OK;
+}
+
+int fdsr_bicubic_u8(fdsr_ctx* c, const uint8_t* lr, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                    uint8_t* out_u8, float* cond, void* stream) {
+  if (!c || !lr) return fail(c, FDSR_E_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_bic(c, w, W);
+  if (rc) return rc;
+  rc = ensure_bic(c, h, H);
+  if (rc) return rc;
+  const fdsr_ctx::BicTab *th = find_bic(c, w, W), *tv = find_bic(c, h, H);
+  const size_t tmp = size_t(B) * h * W * 3;
+  if (tmp > c->bic_tmp_bytes) {
+    cudaFree(c->d_bic_tmp);
+    c->d_bic_tmp = nullptr;
+    CUDA_TRY(c, cudaMalloc(&c->d_bic_tmp, tmp));
+    c->bic_tmp_bytes = tmp;
+  }
+  const int64_t n1 = int64_t(B) * h * W, n2 = int64_t(B) * H * W;
+  bicubic_h_kernel<<<unsigned((n1 + 255) / 256), 256, 0, st>>>(lr, c->d_bic_tmp, th->d_min, th->d_cnt, th->d_taps,
+                                                            th->ksize, B, h, w, W);
+  bicubic_v_kernel<<<unsigned((n2 + 255) / 256), 256, 0, st>>>(c->d_bic_tmp, out_u8, cond, tv->d_min, tv->d_cnt,
+                                                            tv->d_taps, tv->ksize, B, h, H, W);
+  CUDA_TRY(c, cudaGetLastError());
+  c->launches += 2;
+  return FDSR_OK;
+}
+
+int fdsr_super_resolve_u8(fdsr_ctx* c, const uint8_t* lr_host, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                          const float* noise_dev, uint64_t seed, float* sr_out_host, void* stream) {
+  if (!c || !lr_host || !sr_out_host) return fail(c, FDSR_E_INVALID, "null argument");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t in_b = size_t(B) * h * w * 3, out_b = size_t(B) * 3 * H * W * 4;
+  const size_t need_pin = align_up(in_b, 256) + out_b;
+  if (need_pin > c->h_pin_bytes) {
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    c->h_pin = nullptr;
+    CUDA_TRY(c, cudaMallocHost(&c->h_pin, need_pin));
+    c->h_pin_bytes = need_pin;
+  }
+  const size_t need_dev = align_up(in_b, 256) + 2 * out_b;
+  if (need_dev > c->d_stage_bytes) {
+    cudaFree(c->d_stage);
+    c->d_stage = nullptr;
+    CUDA_TRY(c, cudaMalloc(&c->d_stage, need_dev));
+    c->d_stage_bytes = need_dev;
+  }
+  uint8_t* d_lr = c->d_stage;
+  float* d_cond = reinterpret_cast<float*>(c->d_stage + align_up(in_b, 256));
+  float* d_sr = reinterpret_cast<float*>(c->d_stage + align_up(in_b, 256) + out_b);
+  float* h_sr = reinterpret_cast<float*>(c->h_pin + align_up(in_b, 256));
+  memcpy(c->h_pin, lr_host, in_b);
+  CUDA_TRY(c, cudaMemcpyAsync(d_lr, c->h_pin, in_b, cudaMemcpyHostToDevice, st));
+  rc = fdsr_bicubic_u8(c, d_lr, B, h, w, H, W, nullptr, d_cond, stream);
+  if (rc) return rc;
+  rc = fdsr_sample(c, d_cond, noise_dev, seed, d_sr, nullptr, B, H, W, stream);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemcpyAsync(h_sr, d_sr, out_b, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  memcpy(sr_out_host, h_sr, out_b);
+  return FDSR_OK;
+}
+
+int fdsr_sse_u8(fdsr_ctx* c, const float* a, const float* b, int32_t B, int32_t H, int32_t W, double* sse,
+                void* stream) {
+  if (!c || !a || !b || !sse) return fail(c, FDSR_E_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(c, cudaMemsetAsync(sse, 0, size_t(B) * 8, st));
+  const int64_t per = int64_t(3) * H * W;
+  int gx = int((per + 256 * 8 - 1) / (256 * 8));
+  sse_u8_kernel<<<dim3(gx > 0 ? gx : 1, B), 256, 0, st>>>(a, b, sse, per);
+  CUDA_TRY(c, cudaGetLastError());
+  ++c->launches;
+  return FDSR_OK;
+}
+
+int32_t fdsr_debug_num_tensors(const fdsr_ctx* c) { return c ? int32_t(c->tensors.size()) : 0; }
+const char* fdsr_debug_tensor_name(const fdsr_ctx* c, int32_t i) {
+  return (c && i >= 0 && i < int(c->tensors.size())) ? c->tensors[i].name.c_str() : nullptr;
+}
+
+int fdsr_debug_read_tensor(fdsr_ctx* c, const char* name, float* out, int64_t cap, int32_t* C, int32_t* H, int32_t* W,
+                           void* stream) {
+  if (!c || !name || !out) return fail(c, FDSR_E_INVALID, "null argument");
+  if (!c->d_ws) return fail(c, FDSR_E_STATE, "no forward has run");
+  for (const HTensor& t : c->tensors)
+    if (t.name == name) {
+      const int h = c->H >> t.level, w = c->W >> t.level;
+      const int64_t n = int64_t(c->B) * h * w * t.C;
+      if (cap < n) return fail(c, FDSR_E_INVALID, "capacity too small (%lld needed)", (long long)n);
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      if (c->cfg.dtype == FDSR_DTYPE_BF16)
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<unsigned((n + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(c->d_ws + t.off), out, c->B, h * w, t.C);
+      else
+        nhwc_to_nchw_kernel<__half><<<unsigned((n + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const __half*>(c->d_ws + t.off), out, c->B, h * w, t.C);
+      CUDA_TRY(c, cudaGetLastError());
+      if (C) *C = t.C;
+      if (H) *H = h;
+      if (W) *W = w;
+      return FDSR_OK;
+    }
+  return fail(c, FDSR_E_NOTFOUND, "no tensor named %s", name);
+}
+
+int64_t fdsr_launch_count(const fdsr_ctx* c) { return c ? c->launches : 0; }
+double fdsr_unet_flops(const fdsr_ctx* c) { return c ? c->flops_per_px * double(c->B) * c->H * c->W : 0.0; }
+int fdsr_set_use_graph(fdsr_ctx* c, int32_t enable) {
+  if (!c) return FDSR_E_INVALID;
+  c->use_graph = enable != 0;
+  return FDSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// HBM-bound helper kernels of the sampling path: input assembly, posterior update, res2img,
+// CLAM/SLAM gates, PIL-exact bicubic, uint8 SSE, layout conversion for the debug hook.
+// All are coalesced/vectorised elementwise or small-reduction kernels; none needs tensor cores.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include "conv_kernel.cuh"
+
+namespace fdsr {
+
+// ------------------------------------------------------------------------------------------
+// Counter-based Gaussian noise: Philox4x32-10 keyed by the seed, counter = (element/4, stream).
+// Used when the caller does not inject noise (the reference draws torch.randn on the device,
+// diffusion.py:189,207; any N(0,1) stream is an equally valid sample of the same sampler).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream, uint64_t idx4) {
+  const uint4 r = philox4x32_10(make_uint4(uint32_t(idx4), uint32_t(idx4 >> 32), stream, 0x5eedu),
+                                make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = (float(r.x) + 0.5f) * k, u1 = (float(r.y) + 0.5f) * k;
+  const float u2 = (float(r.z) + 0.5f) * k, u3 = (float(r.w) + 0.5f) * k;
+  const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+__global__ void noise_fill_kernel(float* __restrict__ out, int64_t n4, uint64_t seed, uint32_t stream) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i < n4) reinterpret_cast<float4*>(out)[i] = philox_normal4(seed, stream, i);
+}
+
+// ------------------------------------------------------------------------------------------
+// Input assembly: cat([cond, x_t], 1) (diffusion.py:173) as a 16-channel NHWC 16-bit tensor
+// (channels 0-2 cond, 3-5 x_t, 6-15 zero) feeding the stem conv as a single 16-wide K chunk.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ cond, const float* __restrict__ x,
+                                  T* __restrict__ out, int B, int HW) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= int64_t(B) * HW) return;
+  const int b = int(i / HW);
+  const int p = int(i - int64_t(b) * HW);
+  const float* cp = cond + int64_t(b) * 3 * HW + p;
+  const float* xp = x + int64_t(b) * 3 * HW + p;
+  uint4 lo, hi = make_uint4(0u, 0u, 0u, 0u);
+  lo.x = Cvt<T>::pack(cp[0], cp[HW]);
+  lo.y = Cvt<T>::pack(cp[2 * HW], xp[0]);
+  lo.z = Cvt<T>::pack(xp[HW], xp[2 * HW]);
+  lo.w = 0u;
+  uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+  o[0] = lo;
+  o[1] = hi;
+}
+
+// ------------------------------------------------------------------------------------------
+// Posterior update (diffusion.py:157-190), fp32, same operation order as the reference's eager
+// tensor ops (no FMA contraction):
+//   x0 = clamp(a*x - b*eps, -1, 1);  mean = c1*x0 + c2*x;  x_prev = mean + z*sigma
+// z comes from `z` (injected) or from the Philox stream when z == nullptr and use_rng != 0.
+// ------------------------------------------------------------------------------------------
+struct PostCoef {
+  float a, b, c1, c2, sigma;
+};
+__device__ __forceinline__ float post1(float x, float e, float z, const PostCoef& k) {
+  float x0 = __fsub_rn(__fmul_rn(k.a, x), __fmul_rn(k.b, e));
+  x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  const float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, x));
+  return __fadd_rn(mean, __fmul_rn(z, k.sigma));
+}
+__global__ void posterior_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                 const float* __restrict__ z, float* __restrict__ out, int64_t n4,
+                                 PostCoef k, int use_rng, uint64_t seed, uint32_t stream) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n4) return;
+  const float4 xv = reinterpret_cast<const float4*>(x)[i];
+  const float4 ev = reinterpret_cast<const float4*>(eps)[i];
+  float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (z != nullptr) zv = reinterpret_cast<const float4*>(z)[i];
+  else if (use_rng) zv = philox_normal4(seed, stream, i);
+  float4 o;
+  o.x = post1(xv.x, ev.x, zv.x, k);
+  o.y = post1(xv.y, ev.y, zv.y, k);
+  o.z = post1(xv.z, ev.z, zv.z, k);
+  o.w = post1(xv.w, ev.w, zv.w, k);
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+
+// res2img (diffusion.py:275-281): clamp(x,-1,1)/2 + cond.  `out` rows may be strided per sample
+// so the same kernel fills the continous=True trace: out[b*out_bstride + i].
+__global__ void res2img_kernel(const float* __restrict__ x, const float* __restrict__ cond,
+                               float* __restrict__ out, int64_t per_sample, int64_t out_bstride,
+                               int B) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= per_sample * B) return;
+  const int64_t b = i / per_sample, r = i - b * per_sample;
+  const float v = fminf(fmaxf(x[i], -1.0f), 1.0f);
+  out[b * out_bstride + r] = __fadd_rn(__fdiv_rn(v, 2.0f), cond[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// CLAM + SLAM gates of mid[0] (unet.py:123-173, 219-221) on a NHWC 16-bit tensor.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f32_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_f32(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// pool[b][c] = (sum over HW, max over HW); max kept as an order-preserving uint (memset 0 = -inf)
+template <typename T>
+__global__ void clam_pool_kernel(const T* __restrict__ x, float* __restrict__ psum,
+                                 uint32_t* __restrict__ pmax, int HW, int C, int pix_per_block) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, HW);
+  for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
+    const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + (int64_t(b) * HW + p0) * C) + c2;
+    for (int p = p0; p < p1; ++p, xp += C / 2) {
+      const float2 f = Cvt<T>::unpack(*xp);
+      s0 += f.x;
+      s1 += f.y;
+      m0 = fmaxf(m0, f.x);
+      m1 = fmaxf(m1, f.y);
+    }
+    atomicAdd(&psum[b * C + 2 * c2], s0);
+    atomicAdd(&psum[b * C + 2 * c2 + 1], s1);
+    atomicMax(&pmax[b * C + 2 * c2], f32_ordered(m0));
+    atomicMax(&pmax[b * C + 2 * c2 + 1], f32_ordered(m1));
+  }
+}
+
+// gate[b][c] = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max));  W1: [R][C], W2: [C][R]
+__global__ void clam_gate_kernel(const float* __restrict__ psum, const uint32_t* __restrict__ pmax,
+                                 const float* __restrict__ w1, const float* __restrict__ w2,
+                                 float* __restrict__ gate, int HW, int C, int R) {
+  extern __shared__ float sm[];  // avg[C], mx[C], h[2R]
+  float* avg = sm;
+  float* mx = sm + C;
+  float* h = sm + 2 * C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    avg[c] = psum[b * C + c] / float(HW);
+    mx[c] = ordered_f32(pmax[b * C + c]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int r = warp; r < 2 * R; r += nwarp) {
+    const float* v = r < R ? avg : mx;
+    const float* w = w1 + (r % R) * C;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += w[c] * v[c];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) h[r] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, m = 0.f;
+    for (int r = 0; r < R; ++r) {
+      a += w2[c * R + r] * h[r];
+      m += w2[c * R + r] * h[R + r];
+    }
+    gate[b * C + c] = 1.0f / (1.0f + expf(-(a + m)));
+  }
+}
+
+// sp[b][p] = (mean_c, max_c) of gate[c]*x[p][c]; one warp per pixel
+template <typename T>
+__global__ void slam_pool_kernel(const T* __restrict__ x, const float* __restrict__ gate,
+                                 float2* __restrict__ sp, int B, int HW, int C) {
+  const int64_t wid = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= int64_t(B) * HW) return;
+  const int b = int(wid / HW);
+  const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + wid * C);
+  const float* g = gate + b * C;
+  float s = 0.f, m = -INFINITY;
+  for (int c2 = lane; c2 < C / 2; c2 += 32) {
+    const float2 f = Cvt<T>::unpack(xp[c2]);
+    const float a = f.x * g[2 * c2], c = f.y * g[2 * c2 + 1];
+    s += a + c;
+    m = fmaxf(m, fmaxf(a, c));
+  }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (lane == 0) sp[wid] = make_float2(s / float(C), m);
+}
+
+// out[p][c] = sigmoid(conv7x7(sp)[p]) * gate[c] * x[p][c], plus channel-pair statistics of out.
+// One warp per pixel, 8 pixels per block (256 threads); w7: [2][7][7] (avg plane, max plane).
+template <typename T>
+__global__ void slam_apply_kernel(const T* __restrict__ x, const float* __restrict__ gate,
+                                  const float2* __restrict__ sp, const float* __restrict__ w7,
+                                  T* __restrict__ out, double* __restrict__ stats, int H, int W, int C) {
+  extern __shared__ float sacc[];  // [C] pair-interleaved (sum, sumsq) per channel pair
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (p < HW) {
+    const int y = p / W, xq = p - y * W;
+    float a = 0.f;
+    for (int k = lane; k < 98; k += 32) {
+      const int pl = k / 49, kk = k - pl * 49, ky = kk / 7, kx = kk - ky * 7;
+      const int yy = y + ky - 3, xx = xq + kx - 3;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float2 v = sp[int64_t(b) * HW + yy * W + xx];
+        a += w7[k] * (pl == 0 ? v.x : v.y);
+      }
+    }
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    const float sg = 1.0f / (1.0f + expf(-a));
+    const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + (int64_t(b) * HW + p) * C);
+    uint32_t* op = reinterpret_cast<uint32_t*>(out + (int64_t(b) * HW + p) * C);
+    const float* g = gate + b * C;
+    for (int c2 = lane; c2 < C / 2; c2 += 32) {
+      const float2 f = Cvt<T>::unpack(xp[c2]);
+      const float u = sg * (g[2 * c2] * f.x), v = sg * (g[2 * c2 + 1] * f.y);
+      op[c2] = Cvt<T>::pack(u, v);
+      atomicAdd(&sacc[2 * c2], u + v);
+      atomicAdd(&sacc[2 * c2 + 1], u * u + v * v);
+    }
+  }
+  __syncthreads();
+  if (stats != nullptr)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&stats[int64_t(b) * C + i], double(sacc[i]));
+}
+
+// ------------------------------------------------------------------------------------------
+// PIL-exact bicubic (Pillow ImagingResample, 8 bpc): separable, horizontal first, 22-bit fixed
+// point taps, uint8 rounding + clipping after each pass.  bounds/taps are built on the host.
+// ------------------------------------------------------------------------------------------
+constexpr int kBicPrec = 22;
+// in: [B][inH][inW][3] u8 -> out: [B][inH][outW][3] u8
+__global__ void bicubic_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                 const int* __restrict__ xmin, const int* __restrict__ xcnt,
+                                 const int* __restrict__ taps, int ksize, int B, int inH, int inW, int outW) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t total = int64_t(B) * inH * outW;
+  if (i >= total) return;
+  const int xo = int(i % outW);
+  const int64_t row = i / outW;
+  const uint8_t* src = in + (row * inW + xmin[xo]) * 3;
+  const int* k = taps + xo * ksize;
+  int a0 = 1 << (kBicPrec - 1), a1 = a0, a2 = a0;
+  for (int j = 0; j < xcnt[xo]; ++j) {
+    a0 += int(src[3 * j]) * k[j];
+    a1 += int(src[3 * j + 1]) * k[j];
+    a2 += int(src[3 * j + 2]) * k[j];
+  }
+  uint8_t* o = out + i * 3;
+  o[0] = uint8_t(min(max(a0 >> kBicPrec, 0), 255));
+  o[1] = uint8_t(min(max(a1 >> kBicPrec, 0), 255));
+  o[2] = uint8_t(min(max(a2 >> kBicPrec, 0), 255));
+}
+// in: [B][inH][W][3] u8 -> out_u8: [B][outH][W][3] (optional), cond: [B][3][outH][W] fp32 (optional)
+__global__ void bicubic_v_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
+                                 float* __restrict__ cond, const int* __restrict__ ymin,
+                                 const int* __restrict__ ycnt, const int* __restrict__ taps, int ksize,
+                                 int B, int inH, int outH, int W) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t total = int64_t(B) * outH * W;
+  if (i >= total) return;
+  const int x = int(i % W);
+  const int yo = int((i / W) % outH);
+  const int b = int(i / (int64_t(W) * outH));
+  const uint8_t* src = in + ((int64_t(b) * inH + ymin[yo]) * W + x) * 3;
+  const int* k = taps + yo * ksize;
+  int a0 = 1 << (kBicPrec - 1), a1 = a0, a2 = a0;
+  for (int j = 0; j < ycnt[yo]; ++j) {
+    const uint8_t* s = src + int64_t(j) * W * 3;
+    a0 += int(s[0]) * k[j];
+    a1 += int(s[1]) * k[j];
+    a2 += int(s[2]) * k[j];
+  }
+  const int v0 = min(max(a0 >> kBicPrec, 0), 255), v1 = min(max(a1 >> kBicPrec, 0), 255),
+            v2 = min(max(a2 >> kBicPrec, 0), 255);
+  if (out_u8 != nullptr) {
+    uint8_t* o = out_u8 + i * 3;
+    o[0] = uint8_t(v0);
+    o[1] = uint8_t(v1);
+    o[2] = uint8_t(v2);
+  }
+  if (cond != nullptr) {
+    // ToTensor (/255) then *2-1 (data/util.py:66-75), fp32, same operation order
+    const int64_t plane = int64_t(outH) * W;
+    float* c = cond + int64_t(b) * 3 * plane + int64_t(yo) * W + x;
+    c[0] = __fsub_rn(__fmul_rn(__fdiv_rn(float(v0), 255.0f), 2.0f), 1.0f);
+    c[plane] = __fsub_rn(__fmul_rn(__fdiv_rn(float(v1), 255.0f), 2.0f), 1.0f);
+    c[2 * plane] = __fsub_rn(__fmul_rn(__fdiv_rn(float(v2), 255.0f), 2.0f), 1.0f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sum of squared uint8 differences per image after tensor2img quantisation (core/metrics.py:16-42)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quant_u8(float v) {
+  v = fminf(fmaxf(v, -1.0f), 1.0f);
+  v = __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+  return __float2int_rn(__fmul_rn(v, 255.0f));  // numpy .round(): half to even
+}
+__global__ void sse_u8_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                              double* __restrict__ sse, int64_t per_image) {
+  const int img = blockIdx.y;
+  const float* ap = a + img * per_image;
+  const float* bp = b + img * per_image;
+  unsigned long long acc = 0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < per_image;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int d = quant_u8(ap[i]) - quant_u8(bp[i]);
+    acc += (unsigned long long)(d * d);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sse[img], double(acc));
+}
+
+// NHWC 16-bit -> NCHW fp32 (debug hook only)
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int HW, int C) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= int64_t(B) * HW * C) return;
+  const int c = int(i % C);
+  const int64_t bp = i / C;
+  const int b = int(bp / HW);
+  const int p = int(bp - int64_t(b) * HW);
+  float v;
+  if constexpr (Cvt<T>::kFmt == 0) v = __half2float(in[i]);
+  else v = __bfloat162float(in[i]);
+  out[(int64_t(b) * C + c) * HW + p] = v;
+}
+
+}  // namespace fdsr

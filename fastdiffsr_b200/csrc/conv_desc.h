@@ -1,0 +1,83 @@
+// Host/device shared description of one fused convolution launch.
+//
+// Every heavy layer of the UNet (3x3 conv, stride-2 conv, nearest-up conv, 1x1 residual conv,
+// all with optional GroupNorm+Swish on their input, FiLM/bias on their output, residual add and
+// GroupNorm statistics of their output) is ONE launch of conv_gemm_kernel described by a
+// ConvLayer: a list of K-chunks (<= 64 input channels each, from one source tensor), each with a
+// list of taps (a shifted view of the resident input patch x a packed weight blob).
+#pragma once
+#include <cstdint>
+
+namespace fdsr {
+
+constexpr int kMaxChunks = 24;
+constexpr int kMaxTaps = 9;
+constexpr int kMaxSrc = 3;
+
+// Output tile: 32 rows x 8 columns of output pixels = two 128-row MMA tiles (16x8 each).
+constexpr int kTileH = 32;
+constexpr int kTileW = 8;
+constexpr int kPatchW = kTileW + 2;           // input patch pitch in positions
+constexpr int kPatchH = kTileH + 2;
+constexpr int kPatchPos = kPatchW * kPatchH;  // 340 positions
+constexpr int kPlanePos = 341;                // odd => conflict-free 16B stores across channel groups
+constexpr int kPlaneBytes = kPlanePos * 16;
+constexpr int kAStageBytes = 8 * kPlaneBytes;  // 8 channel groups of 8 channels
+
+enum ConvMode : int32_t {
+  kModeNormal = 0,  // stride-1 3x3 (or 1x1 via a single centre tap), zero padding 1
+  kModeUp2x = 1,    // nearest x2 upsample folded into the gather, then stride-1 3x3
+  kModeS2D = 2,     // stride-2 3x3 expressed as 2x2 taps over space-to-depth parity planes
+};
+
+enum OutMode : int32_t {
+  kOutAct = 0,      // 16-bit NHWC activation (+ optional identity residual, + pair statistics)
+  kOutEpsNCHW = 1,  // fp32 NCHW, first `out_c` channels only (final conv)
+};
+
+struct ConvChunk {
+  int32_t src;        // index into ConvLayer::src
+  int32_t c0;         // first channel inside the source tensor
+  int32_t gn;         // 1: GroupNorm+Swish with scale/shift table entries [vc0, vc0+64)
+  int32_t vc0;        // channel offset on the virtual (concatenated) GroupNorm axis
+  int32_t pix_delta;  // extra source pixel offset (parity plane of the space-to-depth view)
+  int32_t ntaps;
+  int32_t w_off;      // byte offset of this chunk's first tap blob inside the layer's weights
+  int32_t tap_pos[kMaxTaps];  // A-operand position offset of each tap (dy*kPatchW + dx)
+};
+
+struct ConvSrc {
+  const void* ptr;      // NHWC 16-bit
+  const double* stats;  // [B][C/2][2] (sum, sum of squares) per channel pair, or null
+  int32_t C;
+  int32_t H, W;         // spatial size of the source tensor
+};
+
+struct ConvLayer {
+  ConvSrc src[kMaxSrc];
+  ConvChunk chunk[kMaxChunks];
+  int32_t nchunks;
+  int32_t ncg;          // 16-byte channel groups per chunk (8, or 2 for the 16-channel stem input)
+  int32_t mode;         // ConvMode
+  int32_t B, H, W;      // output size
+  int32_t N;            // MMA N (padded output channels: 16 / 64 / 128 / 256)
+  // GroupNorm over the virtual concat of src[0..nsrc) (only chunks with gn=1 use it)
+  int32_t gn_C;         // virtual channels (0 = no GroupNorm in this layer)
+  int32_t gn_nsrc;
+  int32_t gn_groups;
+  const float* gamma;   // [gn_C]
+  const float* beta;    // [gn_C]
+  float gn_eps;
+  // epilogue
+  const float* bias;    // [T or 1][N] fp32: conv bias (+ residual-conv bias) (+ FiLM vector of step t)
+  int32_t bias_tstride; // floats between steps (0 when the bias does not depend on t)
+  const void* resid;    // identity residual, NHWC 16-bit with N channels, or null
+  void* out;            // NHWC 16-bit [B][H][W][N]  |  fp32 NCHW [B][out_c][H][W]
+  double* out_stats;    // [B][N/2][2] or null
+  int32_t out_mode;     // OutMode
+  int32_t out_c;
+  const uint8_t* weights;  // packed blobs
+  int32_t tiles_x, tiles_y, ntiles;
+};
+
+}  // namespace fdsr

@@ -1,0 +1,439 @@
+// conv_gemm_kernel: the one heavy kernel of the sampling path (sm_100a only).
+//
+// Implicit-GEMM convolution on tcgen05 tensor cores with fp32 accumulators in TMEM:
+//   M = 256 output pixels per CTA tile (32x8 pixels = two 128-row MMA tiles), N = all output
+//   channels (16/64/128/256), K = taps x input channels, walked in chunks of 64 channels.
+//
+// Warp roles (512 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      MMA issuer (one thread): tcgen05.mma from shared-memory descriptors
+//   warp 1      weight loader (one thread): cp.async.bulk of pre-packed per-tap blobs
+//   warps 4-7   epilogue: tcgen05.ld -> bias/FiLM -> residual -> GroupNorm pair statistics -> store
+//   warps 2,3,8-15  input producers: coalesced 16B global loads of the (32+2)x(8+2) input patch,
+//               GroupNorm scale/shift + Swish in fp32 registers, 16B stores into the resident
+//               patch laid out as [channel group][position][8 ch] (no-swizzle core matrices).
+// The patch is loaded and transformed ONCE per 64-channel chunk and then serves all nine 3x3
+// taps as shifted shared-memory descriptor views (start address + 16 B * (dy*10 + dx), SBO =
+// 160 B), so the A operand is never re-fetched per tap and GroupNorm/Swish/concat/upsample/
+// space-to-depth never touch HBM as separate passes.
+//
+// Reference ops covered (FastDiffSR/model/fastdiffsr_modules/unet.py): Block :89-101 (GroupNorm,
+// Swish, Conv3x3), ResnetBlock :104-120 (FiLM add, residual 1x1 / identity), Downsample :77-83,
+// Upsample :66-74, the skip concatenation :317-321, stem :257-258 and final_conv :297.
+#pragma once
+#include "conv_desc.h"
+#include "ptx.cuh"
+
+namespace fdsr {
+
+constexpr int kConvThreads = 512;
+constexpr int kProdWarps = 10;
+constexpr int kProdThreads = kProdWarps * 32;  // 320
+constexpr int kMaxUnits = 9;                   // ceil(340*8 / 320)
+constexpr int kAStages = 2;
+constexpr int kMaxGnC = 512;
+
+template <int N>
+struct ConvCfg {
+  static constexpr int kAccStride = N < 32 ? 32 : N;        // TMEM columns per 128-row accumulator
+  static constexpr int kAccCols = 2 * kAccStride;           // two MMA tiles per CTA tile
+  static constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = kNumAcc * kAccCols < 32 ? 32 : kNumAcc * kAccCols;
+  static constexpr int kBStageBytes = N * 128;
+  static constexpr int kBStages = N >= 256 ? 4 : (N >= 128 ? 6 : 8);
+  static constexpr int kNcb = N < 32 ? 1 : N / 32;
+  // shared memory carve-up (bytes)
+  static constexpr int kOffA = 0;
+  static constexpr int kOffB = kOffA + kAStages * kAStageBytes;
+  static constexpr int kOffLayer = kOffB + kBStages * kBStageBytes;
+  static constexpr int kOffTable = kOffLayer + ((int(sizeof(ConvLayer)) + 15) / 16) * 16;
+  static constexpr int kOffGstat = kOffTable + kMaxGnC * 8;
+  static constexpr int kOffBias = kOffGstat + 64 * 8;
+  static constexpr int kOffTstat = kOffBias + 256 * 4;
+  static constexpr int kOffBar = kOffTstat + 256 * 4;
+  static constexpr int kNumBar = 2 * kAStages + 2 * kBStages + 2 * kNumAcc;
+  static constexpr int kOffTmem = kOffBar + kNumBar * 8;
+  static constexpr int kSmemBytes = kOffTmem + 16;
+};
+
+template <typename T>
+struct Cvt;
+template <>
+struct Cvt<__half> {
+  static constexpr int kFmt = 0;
+  __device__ static __forceinline__ float2 unpack(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  }
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <>
+struct Cvt<__nv_bfloat16> {
+  static constexpr int kFmt = 1;
+  __device__ static __forceinline__ float2 unpack(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+  }
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+__device__ __forceinline__ float swish_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Sum v[j] over the 32 lanes of a warp for all 32 j at once; lane l returns the total of v[l].
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const float keep = up ? v[j + n] : v[j];
+      const float send = up ? v[j] : v[j + n];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int N, typename T>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
+  using Cfg = ConvCfg<N>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- stage the layer description in shared memory
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(layer_g);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + Cfg::kOffLayer);
+    for (int i = tid; i < int(sizeof(ConvLayer) / 4); i += kConvThreads) dst[i] = src[i];
+  }
+  const ConvLayer& L = *reinterpret_cast<const ConvLayer*>(smem + Cfg::kOffLayer);
+  float2* table = reinterpret_cast<float2*>(smem + Cfg::kOffTable);
+  float2* gstat = reinterpret_cast<float2*>(smem + Cfg::kOffGstat);
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::kOffBias);
+  float* tstat = reinterpret_cast<float*>(smem + Cfg::kOffTstat);
+  const uint32_t bar0 = smem_u32(smem + Cfg::kOffBar);
+  auto bar_a_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_a_empty = [&](int s) { return bar0 + 8u * (kAStages + s); };
+  auto bar_b_full = [&](int s) { return bar0 + 8u * (2 * kAStages + s); };
+  auto bar_b_empty = [&](int s) { return bar0 + 8u * (2 * kAStages + Cfg::kBStages + s); };
+  auto bar_acc_full = [&](int s) { return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + s); };
+  auto bar_acc_empty = [&](int s) {
+    return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + Cfg::kNumAcc + s);
+  };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
+
+  if (tid == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(bar_a_full(s), kProdWarps);
+      mbar_init(bar_a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kBStages; ++s) {
+      mbar_init(bar_b_full(s), 1);
+      mbar_init(bar_b_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kNumAcc; ++s) {
+      mbar_init(bar_acc_full(s), 1);
+      mbar_init(bar_acc_empty(s), 4);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 0) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int ntiles = L.ntiles;
+  const int tiles_per_img = L.tiles_x * L.tiles_y;
+  const int ncg = L.ncg;
+  const uint32_t sA = smem_u32(smem + Cfg::kOffA);
+  const uint32_t sB = smem_u32(smem + Cfg::kOffB);
+
+  if (warp == 0) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, N, Cvt<T>::kFmt);
+      // descriptor high words are constant; low words get the start address added
+      const uint32_t a_hi = ((kPatchW * 16) >> 4) | (1u << 14);
+      const uint32_t a_lo0 = (uint32_t(kPlaneBytes >> 4) << 16);
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16);
+      const int ksteps = ncg >> 1;
+      int as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(bar_acc_empty(acc), accph ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem + acc * Cfg::kAccCols;
+        for (int c = 0; c < L.nchunks; ++c) {
+          const ConvChunk& ck = L.chunk[c];
+          mbar_wait(bar_a_full(as), aph);
+          tc_fence_after();
+          const uint32_t a_base = (sA + as * kAStageBytes) >> 4;
+          for (int tp = 0; tp < ck.ntaps; ++tp) {
+            mbar_wait(bar_b_full(bs), bph);
+            tc_fence_after();
+            const uint32_t b_base = (sB + bs * Cfg::kBStageBytes) >> 4;
+            const uint32_t a_tap = a_base + ck.tap_pos[tp];
+            const uint32_t first = (c | tp) == 0 ? 0u : 1u;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t bd =
+                  (uint64_t(b_hi) << 32) | (b_lo0 | (b_base + ks * 2 * N));
+              const uint32_t a_k = a_tap + ks * 2 * kPlanePos;
+              const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo0 | a_k);
+              const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo0 | (a_k + 16 * kPatchW));
+              const uint32_t accum = first | (ks ? 1u : 0u);
+              umma_f16(d0, ad0, bd, idesc, accum);
+              umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, accum);
+            }
+            umma_commit(bar_b_empty(bs));
+            if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(bar_a_empty(as));
+          if (++as == kAStages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(bar_acc_full(acc));
+        if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== weight loader
+    if (lane == 0) {
+      const uint32_t blob = uint32_t(ncg) * N * 16;
+      int bs = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < L.nchunks; ++c) {
+          const ConvChunk& ck = L.chunk[c];
+          const uint8_t* w = L.weights + ck.w_off;
+          for (int tp = 0; tp < ck.ntaps; ++tp) {
+            mbar_wait(bar_b_empty(bs), bph ^ 1);
+            mbar_arrive_expect_tx(bar_b_full(bs), blob);
+            bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(tp) * blob, blob, bar_b_full(bs));
+            if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================================================== epilogue
+    const int q = warp - 4;            // TMEM lane quarter owned by this warp (== warp % 4)
+    const int et = tid - 128;          // 0..127
+    const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride;
+    for (int i = et; i < N; i += 128) bias_s[i] = bias_g[i];
+    for (int i = et; i < 256; i += 128) tstat[i] = 0.f;
+    named_bar_sync(2, 128);
+    const int m = q * 32 + lane, g = m >> 3, r = m & 7;
+    const bool do_stats = (L.out_stats != nullptr) && (L.out_mode == kOutAct);
+    int acc = 0, accph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int rem = tile - b * tiles_per_img;
+      const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
+      mbar_wait(bar_acc_full(acc), accph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int y = ty * kTileH + mt * 16 + g, x = tx * kTileW + r;
+        const bool valid = y < L.H && x < L.W;
+        const size_t pix = (size_t(b) * L.H + y) * L.W + x;
+        const uint32_t taddr =
+            tmem + (uint32_t(q * 32) << 16) + acc * Cfg::kAccCols + mt * Cfg::kAccStride;
+#pragma unroll 1
+        for (int cb = 0; cb < Cfg::kNcb; ++cb) {
+          uint32_t raw[32];
+          tmem_ld32(taddr + cb * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = __uint_as_float(raw[j]) + ((N >= 32 || j < N) ? bias_s[(cb * 32 + j) & 255] : 0.f);
+          if (L.out_mode == kOutAct) {
+            if (L.resid != nullptr && valid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const T*>(L.resid) + pix * N + cb * 32);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint4 u = rp[k];
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = Cvt<T>::unpack(w4[e]);
+                  v[k * 8 + e * 2] += f.x;
+                  v[k * 8 + e * 2 + 1] += f.y;
+                }
+              }
+            }
+            if (valid) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.out) + pix * N + cb * 32);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 u;
+                u.x = Cvt<T>::pack(v[k * 8 + 0], v[k * 8 + 1]);
+                u.y = Cvt<T>::pack(v[k * 8 + 2], v[k * 8 + 3]);
+                u.z = Cvt<T>::pack(v[k * 8 + 4], v[k * 8 + 5]);
+                u.w = Cvt<T>::pack(v[k * 8 + 6], v[k * 8 + 7]);
+                op[k] = u;
+              }
+            }
+            if (do_stats) {
+              float s[32];
+#pragma unroll
+              for (int p = 0; p < 16; ++p) {
+                const float a = valid ? v[2 * p] : 0.f, c2 = valid ? v[2 * p + 1] : 0.f;
+                s[2 * p] = a + c2;
+                s[2 * p + 1] = a * a + c2 * c2;
+              }
+              const float tot = warp_transpose_reduce32(s, lane);
+              atomicAdd(&tstat[cb * 32 + lane], tot);
+            }
+          } else {  // fp32 NCHW, first out_c channels (final conv -> eps)
+            if (valid && cb == 0) {
+              float* o = reinterpret_cast<float*>(L.out);
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < L.out_c) o[((size_t(b) * L.out_c + c) * L.H + y) * L.W + x] = v[c];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+      if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
+      if (do_stats) {
+        named_bar_sync(2, 128);
+        for (int i = et; i < N; i += 128) {
+          atomicAdd(L.out_stats + size_t(b) * N + i, double(tstat[i]));
+          tstat[i] = 0.f;
+        }
+        named_bar_sync(2, 128);
+      }
+    }
+  } else {
+    // =========================================================== input producers
+    const int pw = warp < 4 ? warp - 2 : warp - 6;  // 0..9
+    const int pidx = pw * 32 + lane;                 // 0..319
+    const int lg = ncg == 8 ? 3 : (ncg == 4 ? 2 : (ncg == 2 ? 1 : 0));
+    const int cg = pidx & (ncg - 1);
+    const int nunits = kPatchPos * ncg;
+    int as = 0, aph = 0, cur_b = -1;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int rem = tile - b * tiles_per_img;
+      const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
+      const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
+
+      // ---- GroupNorm scale/shift table for this sample
+      if (L.gn_C > 0 && b != cur_b) {
+        cur_b = b;
+        named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
+        const int cpg = L.gn_C / L.gn_groups;
+        if (pidx < L.gn_groups) {
+          const int ppg = cpg >> 1, p0 = L.src[0].C >> 1;
+          double S = 0.0, Q = 0.0;
+          for (int pv = pidx * ppg; pv < (pidx + 1) * ppg; ++pv) {
+            const int si = pv < p0 ? 0 : 1;
+            const int pl = pv < p0 ? pv : pv - p0;
+            const double* st = L.src[si].stats + (size_t(b) * (L.src[si].C >> 1) + pl) * 2;
+            S += st[0];
+            Q += st[1];
+          }
+          const double n = double(cpg) * L.src[0].H * L.src[0].W;
+          const double mean = S / n;
+          double var = Q / n - mean * mean;
+          var = var > 0.0 ? var : 0.0;
+          gstat[pidx] = make_float2(float(mean), float(1.0 / sqrt(var + double(L.gn_eps))));
+        }
+        named_bar_sync(1, kProdThreads);
+        for (int c = pidx; c < L.gn_C; c += kProdThreads) {
+          const float2 gs = gstat[c / cpg];
+          const float sc = L.gamma[c] * gs.y;
+          table[c] = make_float2(sc, L.beta[c] - gs.x * sc);
+        }
+        named_bar_sync(1, kProdThreads);
+      }
+
+      // ---- per-thread source pixel offsets of the patch positions it fills (-1 = zero padding)
+      int pixoff[kMaxUnits];
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i) {
+        const int u = pidx + i * kProdThreads;
+        const int pos = u >> lg;
+        const int py = pos / kPatchW, px = pos - py * kPatchW;
+        const int y = y0 + py, x = x0 + px;
+        int off = -1;
+        if (u < nunits && y >= 0 && y < L.H && x >= 0 && x < L.W) {
+          if (L.mode == kModeNormal) off = y * L.W + x;
+          else if (L.mode == kModeUp2x) off = (y >> 1) * (L.W >> 1) + (x >> 1);
+          else if (py <= kTileH && px <= kTileW) off = (2 * y) * (2 * L.W) + 2 * x;
+        }
+        pixoff[i] = off;
+      }
+
+      for (int c = 0; c < L.nchunks; ++c) {
+        const ConvChunk& ck = L.chunk[c];
+        const ConvSrc& s = L.src[ck.src];
+        const int sC = s.C;
+        const T* base = reinterpret_cast<const T*>(s.ptr) +
+                        (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8;
+        uint4 rv[kMaxUnits];
+#pragma unroll
+        for (int i = 0; i < kMaxUnits; ++i) {
+          rv[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (pixoff[i] >= 0) rv[i] = *reinterpret_cast<const uint4*>(base + size_t(pixoff[i]) * sC);
+        }
+        float sc[8], sh[8];
+        if (ck.gn) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 e = table[ck.vc0 + cg * 8 + j];
+            sc[j] = e.x;
+            sh[j] = e.y;
+          }
+        }
+        mbar_wait(bar_a_empty(as), aph ^ 1);
+        const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes;
+#pragma unroll
+        for (int i = 0; i < kMaxUnits; ++i) {
+          const int u = pidx + i * kProdThreads;
+          if (u < nunits) {
+            uint4 o = rv[i];
+            if (ck.gn && pixoff[i] >= 0) {
+              const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+              uint32_t r4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = Cvt<T>::unpack(w4[e]);
+                const float a = swish_f(fmaf(f.x, sc[2 * e], sh[2 * e]));
+                const float bb = swish_f(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
+                r4[e] = Cvt<T>::pack(a, bb);
+              }
+              o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+            }
+            const uint32_t dst = dst0 + uint32_t(u >> lg) * 16;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y),
+                         "r"(o.z), "r"(o.w)
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full(as));
+        if (++as == kAStages) { as = 0; aph ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<Cfg::kTmemCols>(tmem);
+}
+
+}  // namespace fdsr

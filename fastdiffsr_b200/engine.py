@@ -1,0 +1,189 @@
+"""Python owner of one libfdsr context: device memory and streams come from torch, compute from
+the C ABI.  One Engine per (process, GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FdsrConfig, FdsrError
+
+_DTYPES = {"fp16": _lib.DTYPE_FP16, "float16": _lib.DTYPE_FP16, "bf16": _lib.DTYPE_BF16, "bfloat16": _lib.DTYPE_BF16}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, unet_cfg: dict, device, dtype: str = "fp16"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise FdsrError("fastdiffsr_b200 runs on CUDA (sm_100a) devices only; there is no CPU fallback")
+        mults = list(unet_cfg["channel_multiplier"])
+        cfg = FdsrConfig()
+        cfg.in_channel = unet_cfg["in_channel"]
+        cfg.out_channel = unet_cfg["out_channel"]
+        cfg.inner_channel = unet_cfg["inner_channel"]
+        cfg.norm_groups = unet_cfg.get("norm_groups") or 32
+        cfg.n_levels = len(mults)
+        for i, m in enumerate(mults):
+            cfg.channel_mults[i] = m
+        cfg.res_blocks = unet_cfg["res_blocks"]
+        cfg.dtype = _DTYPES[dtype]
+        self.dtype = dtype
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.fdsr_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise FdsrError("fdsr_create: " + self.lib.fdsr_global_error().decode())
+        self.T = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.fdsr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise FdsrError(f"{what}: {self.lib.fdsr_last_error(self._h).decode()} (code {rc})")
+        return rc
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- weights / schedule
+    def load_state_dict(self, sd: dict):
+        items = [(k, v.detach().to("cpu", torch.float32).contiguous()) for k, v in sd.items()
+                 if k.startswith("denoise_fn.")]
+        n = len(items)
+        names = (C.c_char_p * n)(*[k.encode() for k, _ in items])
+        ptrs = (C.c_void_p * n)(*[v.data_ptr() for _, v in items])
+        numels = (C.c_int64 * n)(*[v.numel() for _, v in items])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_load_weights(self._h, names, ptrs, numels, n), "fdsr_load_weights")
+
+    def set_schedule(self, betas):
+        b = np.ascontiguousarray(np.asarray(betas, dtype=np.float64))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_set_schedule(self._h, b.ctypes.data_as(C.POINTER(C.c_double)), len(b)),
+                        "fdsr_set_schedule")
+        self.T = len(b)
+
+    def table(self, name: str):
+        buf = (C.c_double * (self.T + 1))()
+        n = self._check(self.lib.fdsr_get_table(self._h, name.encode(), buf, self.T + 1), "fdsr_get_table")
+        return np.array(buf[:n], dtype=np.float64)
+
+    # ---- compute
+    def _img(self, t, name):
+        if t.device != self.device or t.dtype != torch.float32 or t.dim() != 4 or t.shape[1] != 3:
+            raise FdsrError(f"{name} must be a (B,3,H,W) fp32 tensor on {self.device}")
+        return t.contiguous()
+
+    def unet_forward(self, cond, x_t, t: int):
+        cond, x_t = self._img(cond, "cond"), self._img(x_t, "x_t")
+        B, _, H, W = cond.shape
+        out = torch.empty_like(cond)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_unet_forward(self._h, _ptr(cond), _ptr(x_t), t, _ptr(out), B, H, W,
+                                                   self._stream()), "fdsr_unet_forward")
+        return out
+
+    def posterior_step(self, x_t, eps, z, t: int):
+        x_t, eps = x_t.contiguous(), eps.contiguous()
+        z = z.contiguous() if z is not None else None
+        out = torch.empty_like(x_t)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_posterior_step(self._h, _ptr(x_t), _ptr(eps), _ptr(z), t, _ptr(out),
+                                                     x_t.numel(), self._stream()), "fdsr_posterior_step")
+        return out
+
+    def trace_frames(self):
+        return self.lib.fdsr_trace_frames(self._h)
+
+    def sample(self, cond, noise=None, seed: int = 0, trace: bool = False):
+        cond = self._img(cond, "cond")
+        B, _, H, W = cond.shape
+        if noise is not None:
+            if tuple(noise.shape) != (self.T, B, 3, H, W) or noise.dtype != torch.float32 or noise.device != self.device:
+                raise FdsrError(f"noise must be ({self.T},{B},3,{H},{W}) fp32 on {self.device}")
+            noise = noise.contiguous()
+        out = torch.empty_like(cond)
+        tr = torch.empty((B, self.trace_frames(), 3, H, W), device=self.device, dtype=torch.float32) if trace else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_sample(self._h, _ptr(cond), _ptr(noise), seed, _ptr(out), _ptr(tr), B, H, W,
+                                             self._stream()), "fdsr_sample")
+        return (out, tr) if trace else out
+
+    def bicubic_u8(self, lr_u8, H: int, W: int, want_u8=True, want_cond=True):
+        """lr_u8: (B,h,w,3) uint8 on device -> (u8 (B,H,W,3) | None, cond (B,3,H,W) fp32 | None)."""
+        if lr_u8.dtype != torch.uint8 or lr_u8.dim() != 4 or lr_u8.shape[3] != 3 or lr_u8.device != self.device:
+            raise FdsrError("lr must be (B,h,w,3) uint8 on the engine's device")
+        lr_u8 = lr_u8.contiguous()
+        B, h, w, _ = lr_u8.shape
+        o8 = torch.empty((B, H, W, 3), dtype=torch.uint8, device=self.device) if want_u8 else None
+        oc = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.device) if want_cond else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_bicubic_u8(self._h, _ptr(lr_u8), B, h, w, H, W, _ptr(o8), _ptr(oc),
+                                                 self._stream()), "fdsr_bicubic_u8")
+        return o8, oc
+
+    def super_resolve_u8_host(self, lr_host: np.ndarray, H: int, W: int, noise=None, seed: int = 0):
+        """Host uint8 (B,h,w,3) -> host fp32 (B,3,H,W): H2D, bicubic, T-step sampling, D2H."""
+        lr_host = np.ascontiguousarray(lr_host, dtype=np.uint8)
+        B, h, w, _ = lr_host.shape
+        out = np.empty((B, 3, H, W), dtype=np.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_super_resolve_u8(self._h, lr_host.ctypes.data_as(C.c_void_p), B, h, w, H, W,
+                                                       _ptr(noise), seed, out.ctypes.data_as(C.c_void_p),
+                                                       self._stream()), "fdsr_super_resolve_u8")
+        return out
+
+    def sse_u8(self, a, b):
+        a, b = self._img(a, "a"), self._img(b, "b")
+        B, _, H, W = a.shape
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_sse_u8(self._h, _ptr(a), _ptr(b), B, H, W, _ptr(out), self._stream()),
+                        "fdsr_sse_u8")
+        return out
+
+    # ---- hooks
+    def tensor_names(self):
+        n = self.lib.fdsr_debug_num_tensors(self._h)
+        return [self.lib.fdsr_debug_tensor_name(self._h, i).decode() for i in range(n)]
+
+    def read_tensor(self, name: str, B: int, max_elems: int):
+        buf = torch.empty(max_elems, dtype=torch.float32, device=self.device)
+        c, h, w = C.c_int32(), C.c_int32(), C.c_int32()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_debug_read_tensor(self._h, name.encode(), _ptr(buf), max_elems, C.byref(c),
+                                                        C.byref(h), C.byref(w), self._stream()), "fdsr_debug_read_tensor")
+        n = B * c.value * h.value * w.value
+        return buf[:n].view(B, c.value, h.value, w.value)
+
+    def launch_count(self):
+        return int(self.lib.fdsr_launch_count(self._h))
+
+    def unet_flops(self):
+        return float(self.lib.fdsr_unet_flops(self._h))
+
+    def reserve(self, B, H, W):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_reserve(self._h, B, H, W), "fdsr_reserve")
+
+    def workspace_bytes(self):
+        return int(self.lib.fdsr_workspace_bytes(self._h))
+
+    def set_use_graph(self, enable: bool):
+        self.lib.fdsr_set_use_graph(self._h, 1 if enable else 0)
