@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the FastDiffSR T=20 conditional sampling path on B200 (see BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (libfdsr through define_G)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+A "step" is one complete T=20 super_resolution of one batch of LR images (x4 64->256, 16 images
+per GPU = BASELINE configs[1]); metric = SR images / s.  For N > 1 launch under torchrun: the
+batch is sharded by image (weak scaling: 16 images per rank), each rank runs the whole loop on
+its shard, and NCCL is used once per step to all-gather the SR outputs and all-reduce the PSNR
+accumulators.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_IMAGE_STEP_256 = 268.31e9   # BASELINE.md section 2 (2*MAC, padding counted)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU")
+    ap.add_argument("--lr", type=int, default=64, help="LR resolution")
+    ap.add_argument("--hr", type=int, default=256, help="HR resolution")
+    ap.add_argument("--dtype", default=os.environ.get("FDSR_DTYPE", "fp16"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synthetic_lr(batch, res, seed):
+    """uint8 LR images: uniform noise smoothed by a 5x5 box blur."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randint(0, 256, (batch, 3, res, res), generator=g).float()
+    a = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(a, (2, 2, 2, 2), mode="reflect"), 5, 1)
+    return a.round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    return 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def run_reference(args, rank):
+    """The reference algorithm (CPU oracle port of GaussianDiffusion.super_resolution) on host cores:
+    each step is a bounded sample of the workload — T=20 sampling of ONE 64->256 image."""
+    if rank != 0:
+        return
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fdsr_oracle as O
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = dict(O.DEFAULT_UNET)
+    sd = O.make_state_dict(cfg, seed=0)
+    tab = O.schedule_tables(O.make_beta_schedule(**O.DEFAULT_SCHEDULE))
+    lr = synthetic_lr(1, args.lr, 1)
+    cond = O.u8_to_cond(O.pil_bicubic_u8(lr[0].numpy(), args.hr, args.hr)[None])
+    noises = torch.randn(20, 1, 3, args.hr, args.hr, generator=torch.Generator().manual_seed(2))
+    for _ in range(args.warmup):
+        O.unet_forward(sd, cfg, torch.cat([cond, noises[0]], 1), torch.full((1, 1), 0.5))  # warm threads/allocator
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.sample_loop(sd, cfg, tab, cond, noises)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 1.0 / dt
+    sample = f"T=20 sampling of 1 image {args.lr}->{args.hr} per step, fp32, torch CPU {cores} threads"
+    out = {"impl": "reference", "metric": "sr_images_per_s_T20", "value": val, "unit": "images/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"FastDiffSR x{args.hr // args.lr} {args.lr}->{args.hr} T=20 sampling, "
+                                  f"batch {args.batch}/GPU (reference arm: bounded sample of 1 image per step)"},
+           "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fastdiffsr_b200 as F
+    from fastdiffsr_b200 import parallel as P
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a B200: there is no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B, h, H = args.batch, args.lr, args.hr
+    name = "sr_fastdiffsr_test_32_256" if h == 32 else ("sr_fastdiffsr_infer_x4" if H == 512 else "sr_fastdiffsr_test_64_256")
+    opt = F.config.default_config(name)
+    opt["model"]["compute_dtype"] = args.dtype
+    torch.manual_seed(0)                       # random-init weights of the named architecture
+    netG = F.define_G(opt).to(dev)
+    netG.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], dev)
+    netG.eval()
+    eng = netG.engine()
+    T = netG.num_timesteps
+
+    lr_host = synthetic_lr(B, h, 1 + rank).numpy()
+    lr_dev = torch.from_numpy(lr_host).to(dev)
+    _, cond = eng.bicubic_u8(lr_dev, H, H, want_u8=False)
+    g = torch.Generator().manual_seed(100 + rank)
+    hr = (cond.cpu() + 0.1 * torch.nn.functional.avg_pool2d(torch.randn(B, 3, H, H, generator=g), 3, 1, 1)).clamp(-1, 1).to(dev)
+    acc = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def step_device(i):
+        sr = netG.super_resolution(cond, False, seed=1000 + i)
+        sse = eng.sse_u8(sr, hr)
+        psnr = P.psnr_from_sse(sse, 3 * H * H)
+        local = torch.stack([sse.sum(), psnr.sum(), torch.tensor(float(B), dtype=torch.float64, device=dev)])
+        if world > 1:
+            full = P.gather_batch(sr, B * world)          # all-gather of the SR shards
+            P.reduce_sums(local)                           # all-reduce of the metric sums
+            del full
+        acc.add_(local)
+        return sr
+
+    def step_host(i):
+        return eng.super_resolve_u8_host(lr_host, H, H, seed=2000 + i)
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, eng.launch_count() - l0
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    ms_dev, launches = timed(step_device, args.steps, max(args.warmup, 3))
+    ms_e2e, _ = timed(step_host, max(2, min(args.steps, 5)), 1)
+    clk = clocks.stop() if clocks else None
+    value = B * world / (ms_dev / 1e3)
+    e2e = B * world / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (conv_gemm_kernel, tensor-bound): CUDA events around each
+    # launch of a full UNet evaluation at the benchmark shape, averaged over repetitions
+    prof = eng.profile_unet(T // 2, reps=5)
+    conv = [(n, ms, fl) for n, ms, fl in prof if fl > 0]
+    conv_ms = sum(ms for _, ms, _ in conv)
+    conv_fl = sum(fl for _, _, fl in conv)
+    peak, peak_src = measured_peaks()
+    achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+    flop_per_image = eng.unet_flops() / B * T
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "conv_gemm_kernel (all conv layers of one UNet step)",
+                "launches_profiled": len(conv), "conv_ms_per_unet_step": conv_ms,
+                "other_ms_per_unet_step": sum(ms for _, ms, fl in prof if fl == 0),
+                "whole_step_frac": value / world * flop_per_image / 1e12 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import fdsr_oracle as O
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        sd = {k: v.detach().cpu() for k, v in netG.state_dict().items() if k.startswith("denoise_fn.")}
+        cfg = dict(O.DEFAULT_UNET)
+        tab = O.schedule_tables(O.make_beta_schedule(**O.DEFAULT_SCHEDULE))
+        c1 = cond[:1].cpu()
+        nz = torch.randn(T, 1, 3, H, H, generator=torch.Generator().manual_seed(2))
+        O.unet_forward(sd, cfg, torch.cat([c1, nz[0]], 1), torch.full((1, 1), 0.5))
+        t0 = time.perf_counter()
+        ref = O.sample_loop(sd, cfg, tab, c1, nz)
+        dt = time.perf_counter() - t0
+        ours = eng.sample(cond[:1].contiguous(), noise=nz.to(dev)).cpu()
+        cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"T=20 sampling of 1 image {h}->{H}, fp32 torch CPU, {dt:.1f} s",
+               "parity_rel_l2_vs_gpu": ((ours - ref).norm() / ref.norm()).item()}
+
+    if rank == 0:
+        out = {"metric": "sr_images_per_s_T20", "value": value, "unit": "images/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+               "config": {"workload": f"FastDiffSR x{H // h} {h}->{H} T={T} sampling, batch {B}/GPU "
+                                      f"(BASELINE configs[1])" if (h, H, B) == (64, 256, 16) else
+                                      f"FastDiffSR x{H // h} {h}->{H} T={T} sampling, batch {B}/GPU",
+                          "global_batch": B * world, "parallelism": f"image-sharded x{world}",
+                          "l2": "working set per step (activations %.1f GiB) exceeds the 126 MB L2; no flush needed"
+                                % (eng.workspace_bytes() / 2 ** 30),
+                          "ms_per_unet_step": ms_dev / T, "noise": "on-device Philox (value), same (e2e)"},
+               "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(lr_host.nbytes),
+                       "d2h_bytes_per_step": int(B * 3 * H * H * 4), "ms_per_step": ms_e2e,
+                       "api": "Engine.super_resolve_u8_host -> fdsr_super_resolve_u8 (uint8 LR host -> fp32 SR host)"},
+               "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+               "psnr_mean_vs_synthetic_hr": (acc[1] / acc[2]).item() if acc[2].item() > 0 else None}
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,11 @@ _SIGS = {
     "fdsr_debug_tensor_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
     "fdsr_debug_read_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
+    "fdsr_debug_num_ops": (C.c_int32, [C.c_void_p]),
+    "fdsr_debug_op_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
+    "fdsr_debug_op_flops": (C.c_double, [C.c_void_p, C.c_int32]),
+    "fdsr_debug_profile_unet": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32,
+                                          C.c_void_p]),
     "fdsr_launch_count": (C.c_int64, [C.c_void_p]),
     "fdsr_unet_flops": (C.c_double, [C.c_void_p]),
     "fdsr_set_use_graph": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -43,3 +43,46 @@ def load_config(path: str, phase: str = "val", gpu_ids=None):
     gl = opt.get("gpu_ids") or []
     opt["distributed"] = len(gl) > 1
     return dict_to_nonedict(opt)
+
+
+_SHAPES = {
+    # name: (l_resolution, r_resolution, train dataroot, val dataroot)  — the reference's shipped configs
+    "sr_fastdiffsr_test_64_256": (64, 256, "dataset/Train_64_256", "dataset/Test_Toronto_64_256"),
+    "sr_fastdiffsr_train_64_256": (64, 256, "dataset/Train_64_256", "dataset/Test_Potsdam_64_256"),
+    "sr_fastdiffsr_test_32_256": (32, 256, "dataset/Train_32_256", "dataset/Test_Toronto_32_256"),
+    "sr_fastdiffsr_train_32_256": (32, 256, "dataset/Train_32_256", "dataset/Test_Potsdam_32_256"),
+    "sr_fastdiffsr_infer_x4": (128, 512, "dataset/Train_64_256", "dataset/UCM_128_512"),
+    "sr_fastdiffsr_infer_128_512": (128, 512, "dataset/Train_64_256", "dataset/UCM_128_512"),
+}
+
+
+def default_config(name: str = "sr_fastdiffsr_test_64_256", phase: str = "val", gpu_ids=(0,)):
+    """Programmatic equivalent of the reference's config/<name>.json for every key define_G and the
+    sampling path consume (config/sr_fastdiffsr_test_64_256.json:52-86): same UNet widths, T=20
+    linear_cosine schedule, conditional 3-channel diffusion.  Lets the package run where the
+    reference tree (and its JSON files) is absent."""
+    name = name[:-5] if name.endswith(".json") else name
+    if name not in _SHAPES:
+        raise KeyError(f"unknown config {name!r}; known: {sorted(_SHAPES)}")
+    lres, rres, train_root, val_root = _SHAPES[name]
+    sched = dict(schedule="linear_cosine", n_timestep=20, linear_start=1e-6, linear_end=1e-2)
+    # the x4 train/infer configs condition on 64->256 training crops; inference runs fully convolutionally
+    train_l = 64 if lres == 128 else lres
+    opt = {
+        "name": name, "phase": phase, "gpu_ids": list(gpu_ids),
+        "datasets": {
+            "train": {"name": "Train", "mode": "LRHR", "dataroot": train_root, "datatype": "img",
+                      "l_resolution": train_l, "r_resolution": 256, "batch_size": 4},
+            "val": {"name": "Test", "mode": "LRHR", "dataroot": val_root, "datatype": "img",
+                    "l_resolution": lres, "r_resolution": rres},
+        },
+        "model": {
+            "which_model_G": "fastdiffsr", "finetune_norm": False,
+            "unet": {"in_channel": 6, "out_channel": 3, "inner_channel": 64, "channel_multiplier": [1, 2, 4, 4],
+                     "attn_res": [16], "res_blocks": 2, "dropout": 0.2},
+            "beta_schedule": {"train": dict(sched), "val": dict(sched)},
+            "diffusion": {"image_size": 256, "channels": 3, "conditional": True},
+        },
+    }
+    opt["distributed"] = len(opt["gpu_ids"]) > 1
+    return dict_to_nonedict(opt)

@@ -535,7 +535,7 @@ int upload_layers(fdsr_ctx* c) {
     for (int s = 0; s < k.nsrc; ++s) {
       const HTensor& t = c->tensors[k.src[s]];
       l.src[s].ptr = c->d_ws + t.off;
-      l.src[s].stats = t.stats ? reinterpret_cast<const double*>(c->d_ws + t.stats_off) : nullptr;
+      l.src[s].stats = t.stats ? reinterpret_cast<const unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
       l.src[s].C = t.C;
       l.src[s].H = H >> t.level;
       l.src[s].W = W >> t.level;
@@ -571,7 +571,7 @@ int upload_layers(fdsr_ctx* c) {
     if (k.out_mode == kOutAct) {
       const HTensor& t = c->tensors[k.out];
       l.out = c->d_ws + t.off;
-      l.out_stats = t.stats ? reinterpret_cast<double*>(c->d_ws + t.stats_off) : nullptr;
+      l.out_stats = t.stats ? reinterpret_cast<unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
     } else {
       l.out = c->d_ws + c->off_eps;
     }
@@ -631,7 +631,7 @@ int launch_attn(fdsr_ctx* c, const HAttn& a, cudaStream_t st) {
   const int h = c->H >> ti.level, w = c->W >> ti.level, HW = h * w, C = a.C, R = C / 16;
   const T* x = reinterpret_cast<const T*>(c->d_ws + ti.off);
   T* y = reinterpret_cast<T*>(c->d_ws + to.off);
-  float* psum = reinterpret_cast<float*>(c->d_ws + c->off_psum);
+  unsigned long long* psum = reinterpret_cast<unsigned long long*>(c->d_ws + c->off_psum);
   uint32_t* pmax = reinterpret_cast<uint32_t*>(c->d_ws + c->off_pmax);
   float* gate = reinterpret_cast<float*>(c->d_ws + c->off_gate);
   float2* sp = reinterpret_cast<float2*>(c->d_ws + c->off_sp);
@@ -641,8 +641,8 @@ int launch_attn(fdsr_ctx* c, const HAttn& a, cudaStream_t st) {
                                                          c->d_params + a.w2_off, gate, HW, C, R);
   const int64_t nwarp = int64_t(c->B) * HW;
   slam_pool_kernel<T><<<unsigned((nwarp * 32 + 255) / 256), 256, 0, st>>>(x, gate, sp, c->B, HW, C);
-  slam_apply_kernel<T><<<dim3((HW + 7) / 8, c->B), 256, C * 4, st>>>(
-      x, gate, sp, c->d_params + a.w7_off, y, reinterpret_cast<double*>(c->d_ws + to.stats_off), h, w, C);
+  slam_apply_kernel<T><<<dim3((HW + 7) / 8, c->B), 256, 8 * C * 4, st>>>(
+      x, gate, sp, c->d_params + a.w7_off, y, reinterpret_cast<unsigned long long*>(c->d_ws + to.stats_off), h, w, C);
   CUDA_TRY(c, cudaGetLastError());
   c->launches += 4;
   return FDSR_OK;
@@ -680,17 +680,17 @@ int check_ready(fdsr_ctx* c) {
 }
 
 int posterior_launch(fdsr_ctx* c, const float* x, const float* eps, const float* z, int t, float* out,
-                     int64_t numel, int use_rng, uint64_t seed, cudaStream_t st) {
+                     int64_t numel, const uint64_t* seed, cudaStream_t st) {
   if (numel % 4) return fail(c, FDSR_E_INVALID, "numel must be a multiple of 4");
   const int64_t n4 = numel / 4;
-  posterior_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(x, eps, z, out, n4, c->post[t], use_rng, seed,
-                                                             uint32_t(t));
+  posterior_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(x, eps, z, out, n4, c->post[t], seed, uint32_t(t));
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
   return FDSR_OK;
 }
 
-int sample_enqueue(fdsr_ctx* c, const float* noise, uint64_t seed, float* trace, cudaStream_t st) {
+int sample_enqueue(fdsr_ctx* c, const float* noise, float* trace, cudaStream_t st) {
+  const uint64_t* seed = reinterpret_cast<const uint64_t*>(c->d_ws + c->off_seed);
   const int T = c->T, B = c->B;
   const int64_t per = int64_t(3) * c->H * c->W, numel = per * B;
   float* x = reinterpret_cast<float*>(c->d_ws + c->off_x);
@@ -716,7 +716,7 @@ int sample_enqueue(fdsr_ctx* c, const float* noise, uint64_t seed, float* trace,
     int rc = unet_dispatch(c, t, st);
     if (rc) return rc;
     const float* z = (noise && t > 0) ? noise + int64_t(k + 1) * numel : nullptr;
-    rc = posterior_launch(c, x, eps, z, t, x, numel, (!noise && t > 0) ? 1 : 0, seed, st);
+    rc = posterior_launch(c, x, eps, z, t, x, numel, (!noise && t > 0) ? seed : nullptr, st);
     if (rc) return rc;
     if (trace && t % inter == 0) {
       res2img_kernel<<<gb, 256, 0, st>>>(x, cond, trace + per * frame, per, per * nfr, B);
@@ -958,7 +958,7 @@ int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
     lmin = c->tensors[a.in].level < lmin ? c->tensors[a.in].level : lmin;
   }
   c->off_psum = off;
-  off += size_t(B) * cmax * 4;
+  off += size_t(B) * cmax * 8;
   c->off_pmax = off;
   off += size_t(B) * cmax * 4;
   off = align_up(off, 256);
@@ -976,6 +976,8 @@ int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
   off += img;
   c->off_sr = off;
   off += img;
+  c->off_seed = off;
+  off += 256;
   if (c->d_ws) cudaFree(c->d_ws);
   c->d_ws = nullptr;
   CUDA_TRY(c, cudaMalloc(&c->d_ws, off));
@@ -1016,7 +1018,7 @@ int fdsr_posterior_step(fdsr_ctx* c, const float* xt, const float* eps, const fl
   if (!c || !xt || !eps || !out) return fail(c, FDSR_E_INVALID, "null argument");
   if (c->T == 0) return fail(c, FDSR_E_STATE, "fdsr_set_schedule has not been called");
   if (t < 0 || t >= c->T) return fail(c, FDSR_E_INVALID, "t out of range");
-  return posterior_launch(c, xt, eps, t > 0 ? z : nullptr, t, out, numel, 0, 0, static_cast<cudaStream_t>(stream));
+  return posterior_launch(c, xt, eps, t > 0 ? z : nullptr, t, out, numel, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int32_t fdsr_trace_frames(const fdsr_ctx* c) {
@@ -1038,9 +1040,9 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t bytes = size_t(B) * 3 * H * W * 4;
   CUDA_TRY(c, cudaMemcpyAsync(c->d_ws + c->off_cond, cond, bytes, cudaMemcpyDeviceToDevice, st));
-  // The Philox seed is a kernel argument, so RNG-mode graphs are keyed on it as well via `noise`
-  // == nullptr + re-capture when the seed changes (cheap next to 20 UNet steps).
-  static thread_local uint64_t last_seed = 0;
+  // the Philox seed is read from device memory, so one captured graph serves every seed
+  set_seed_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint64_t*>(c->d_ws + c->off_seed), seed);
+  ++c->launches;
   const bool want_graph = c->use_graph;
   if (want_graph) {
     if (c->layers_dirty) {
@@ -1048,7 +1050,7 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
       if (rc) return rc;
     }
     const bool hit = c->graph && c->gkey.B == B && c->gkey.H == H && c->gkey.W == W && c->gkey.noise == noise &&
-                     c->gkey.trace == trace && (noise || last_seed == seed);
+                     c->gkey.trace == trace;
     if (!hit) {
       if (c->graph) {
         cudaGraphExecDestroy(c->graph);
@@ -1059,7 +1061,7 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
       // make sure every kernel attribute is set before capture (cudaFuncSetAttribute is not capturable)
       const int64_t l0 = c->launches;
       CUDA_TRY(c, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      rc = sample_enqueue(c, noise, seed, trace, cs);
+      rc = sample_enqueue(c, noise, trace, cs);
       cudaGraph_t g = nullptr;
       cudaError_t e = cudaStreamEndCapture(cs, &g);
       cudaStreamDestroy(cs);
@@ -1076,7 +1078,6 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
       c->gkey.W = W;
       c->gkey.noise = noise;
       c->gkey.trace = trace;
-      last_seed = seed;
       c->launches = l0;  // captured, not yet launched
     }
     CUDA_TRY(c, cudaGraphLaunch(c->graph, st));
@@ -1085,7 +1086,7 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
     for (const HOp& op : c->ops) per_unet += op.kind == 0 ? 1 : 4;
     c->launches += int64_t(c->T) * (per_unet + 1) + 1 + (noise ? 0 : 1) + (trace ? fdsr_trace_frames(c) : 0);
   } else {
-    rc = sample_enqueue(c, noise, seed, trace, st);
+    rc = sample_enqueue(c, noise, trace, st);
     if (rc) return rc;
   }
   CUDA_TRY(c, cudaMemcpyAsync(sr_out, c->d_ws + c->off_sr, bytes, cudaMemcpyDeviceToDevice, st));
@@ -1196,6 +1197,61 @@ int fdsr_debug_read_tensor(fdsr_ctx* c, const char* name, float* out, int64_t ca
       return FDSR_OK;
     }
   return fail(c, FDSR_E_NOTFOUND, "no tensor named %s", name);
+}
+
+int32_t fdsr_debug_num_ops(const fdsr_ctx* c) { return c ? int32_t(c->ops.size()) : 0; }
+const char* fdsr_debug_op_name(const fdsr_ctx* c, int32_t i) {
+  if (!c || i < 0 || i >= int(c->ops.size())) return nullptr;
+  const HOp& op = c->ops[i];
+  return op.kind == 0 ? c->convs[op.idx].name.c_str() : "mid.0.clam_slam";
+}
+double fdsr_debug_op_flops(const fdsr_ctx* c, int32_t i) {
+  if (!c || i < 0 || i >= int(c->ops.size()) || c->ops[i].kind != 0) return 0.0;
+  const HConv& k = c->convs[c->ops[i].idx];
+  const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
+  double macs = 0.0;
+  for (const HChunk& ch : k.chunks) macs += double(ch.taps.size()) * ch.creal;
+  return 2.0 * macs * k.cout * double(c->B) * (c->H >> lvl) * (c->W >> lvl);
+}
+
+int fdsr_debug_profile_unet(fdsr_ctx* c, int32_t t, int32_t reps, float* ms_out_host, int32_t cap, void* stream) {
+  if (!c || !ms_out_host) return fail(c, FDSR_E_INVALID, "null argument");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!c->d_ws) return fail(c, FDSR_E_STATE, "run fdsr_unet_forward / fdsr_sample once first");
+  const int nops = int(c->ops.size());
+  if (cap < nops) return fail(c, FDSR_E_INVALID, "capacity too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->layers_dirty) {
+    rc = upload_layers(c);
+    if (rc) return rc;
+  }
+  std::vector<cudaEvent_t> ev(size_t(nops) * 2 * reps);
+  for (auto& e : ev) CUDA_TRY(c, cudaEventCreate(&e));
+  const bool bf = c->cfg.dtype == FDSR_DTYPE_BF16;
+  for (int r = 0; r < reps; ++r) {
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ws + c->stats_off, 0, c->stats_bytes, st));
+    for (int i = 0; i < nops; ++i) {
+      const HOp& op = c->ops[i];
+      CUDA_TRY(c, cudaEventRecord(ev[(size_t(r) * nops + i) * 2], st));
+      if (op.kind == 0) rc = bf ? launch_conv<__nv_bfloat16>(c, op.idx, t, st) : launch_conv<__half>(c, op.idx, t, st);
+      else rc = bf ? launch_attn<__nv_bfloat16>(c, c->attns[op.idx], st) : launch_attn<__half>(c, c->attns[op.idx], st);
+      if (rc) return rc;
+      CUDA_TRY(c, cudaEventRecord(ev[(size_t(r) * nops + i) * 2 + 1], st));
+    }
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  for (int i = 0; i < nops; ++i) {
+    double acc = 0.0;
+    for (int r = 0; r < reps; ++r) {
+      float ms = 0.f;
+      CUDA_TRY(c, cudaEventElapsedTime(&ms, ev[(size_t(r) * nops + i) * 2], ev[(size_t(r) * nops + i) * 2 + 1]));
+      acc += ms;
+    }
+    ms_out_host[i] = float(acc / reps);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return nops;
 }
 
 int64_t fdsr_launch_count(const fdsr_ctx* c) { return c ? c->launches : 0; }

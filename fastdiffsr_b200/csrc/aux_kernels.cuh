@@ -38,9 +38,13 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream,
   return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
 }
 
-__global__ void noise_fill_kernel(float* __restrict__ out, int64_t n4, uint64_t seed, uint32_t stream) {
+// The seed lives in device memory so that a captured CUDA graph can be replayed with a new seed.
+__global__ void set_seed_kernel(uint64_t* slot, uint64_t seed) { *slot = seed; }
+
+__global__ void noise_fill_kernel(float* __restrict__ out, int64_t n4, const uint64_t* __restrict__ seed,
+                                  uint32_t stream) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i < n4) reinterpret_cast<float4*>(out)[i] = philox_normal4(seed, stream, i);
+  if (i < n4) reinterpret_cast<float4*>(out)[i] = philox_normal4(*seed, stream, i);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -70,7 +74,7 @@ __global__ void pack_input_kernel(const float* __restrict__ cond, const float* _
 // Posterior update (diffusion.py:157-190), fp32, same operation order as the reference's eager
 // tensor ops (no FMA contraction):
 //   x0 = clamp(a*x - b*eps, -1, 1);  mean = c1*x0 + c2*x;  x_prev = mean + z*sigma
-// z comes from `z` (injected) or from the Philox stream when z == nullptr and use_rng != 0.
+// z comes from `z` (injected) or from the Philox stream when z == nullptr and seed != nullptr.
 // ------------------------------------------------------------------------------------------
 struct PostCoef {
   float a, b, c1, c2, sigma;
@@ -83,14 +87,14 @@ __device__ __forceinline__ float post1(float x, float e, float z, const PostCoef
 }
 __global__ void posterior_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                                  const float* __restrict__ z, float* __restrict__ out, int64_t n4,
-                                 PostCoef k, int use_rng, uint64_t seed, uint32_t stream) {
+                                 PostCoef k, const uint64_t* __restrict__ seed, uint32_t stream) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n4) return;
   const float4 xv = reinterpret_cast<const float4*>(x)[i];
   const float4 ev = reinterpret_cast<const float4*>(eps)[i];
   float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (z != nullptr) zv = reinterpret_cast<const float4*>(z)[i];
-  else if (use_rng) zv = philox_normal4(seed, stream, i);
+  else if (seed != nullptr) zv = philox_normal4(*seed, stream, i);
   float4 o;
   o.x = post1(xv.x, ev.x, zv.x, k);
   o.y = post1(xv.y, ev.y, zv.y, k);
@@ -124,7 +128,7 @@ __device__ __forceinline__ float ordered_f32(uint32_t u) {
 
 // pool[b][c] = (sum over HW, max over HW); max kept as an order-preserving uint (memset 0 = -inf)
 template <typename T>
-__global__ void clam_pool_kernel(const T* __restrict__ x, float* __restrict__ psum,
+__global__ void clam_pool_kernel(const T* __restrict__ x, unsigned long long* __restrict__ psum,
                                  uint32_t* __restrict__ pmax, int HW, int C, int pix_per_block) {
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
@@ -139,15 +143,16 @@ __global__ void clam_pool_kernel(const T* __restrict__ x, float* __restrict__ ps
       m0 = fmaxf(m0, f.x);
       m1 = fmaxf(m1, f.y);
     }
-    atomicAdd(&psum[b * C + 2 * c2], s0);
-    atomicAdd(&psum[b * C + 2 * c2 + 1], s1);
+    // order-independent fixed-point accumulation (bitwise reproducible)
+    atomicAdd(&psum[b * C + 2 * c2], static_cast<unsigned long long>(__double2ll_rn(double(s0) * kStatScale)));
+    atomicAdd(&psum[b * C + 2 * c2 + 1], static_cast<unsigned long long>(__double2ll_rn(double(s1) * kStatScale)));
     atomicMax(&pmax[b * C + 2 * c2], f32_ordered(m0));
     atomicMax(&pmax[b * C + 2 * c2 + 1], f32_ordered(m1));
   }
 }
 
 // gate[b][c] = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max));  W1: [R][C], W2: [C][R]
-__global__ void clam_gate_kernel(const float* __restrict__ psum, const uint32_t* __restrict__ pmax,
+__global__ void clam_gate_kernel(const unsigned long long* __restrict__ psum, const uint32_t* __restrict__ pmax,
                                  const float* __restrict__ w1, const float* __restrict__ w2,
                                  float* __restrict__ gate, int HW, int C, int R) {
   extern __shared__ float sm[];  // avg[C], mx[C], h[2R]
@@ -156,7 +161,7 @@ __global__ void clam_gate_kernel(const float* __restrict__ psum, const uint32_t*
   float* h = sm + 2 * C;
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    avg[c] = psum[b * C + c] / float(HW);
+    avg[c] = float(double(static_cast<long long>(psum[b * C + c])) * (1.0 / kStatScale) / double(HW));
     mx[c] = ordered_f32(pmax[b * C + c]);
   }
   __syncthreads();
@@ -209,14 +214,14 @@ __global__ void slam_pool_kernel(const T* __restrict__ x, const float* __restric
 template <typename T>
 __global__ void slam_apply_kernel(const T* __restrict__ x, const float* __restrict__ gate,
                                   const float2* __restrict__ sp, const float* __restrict__ w7,
-                                  T* __restrict__ out, double* __restrict__ stats, int H, int W, int C) {
-  extern __shared__ float sacc[];  // [C] pair-interleaved (sum, sumsq) per channel pair
+                                  T* __restrict__ out, unsigned long long* __restrict__ stats, int H, int W,
+                                  int C) {
+  extern __shared__ float sacc[];  // [8 warps][C]: (sum, sumsq) per channel pair, one row per pixel/warp
   const int b = blockIdx.y;
   const int HW = H * W;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + warp;
+  float* row = sacc + warp * C;
   if (p < HW) {
     const int y = p / W, xq = p - y * W;
     float a = 0.f;
@@ -237,13 +242,19 @@ __global__ void slam_apply_kernel(const T* __restrict__ x, const float* __restri
       const float2 f = Cvt<T>::unpack(xp[c2]);
       const float u = sg * (g[2 * c2] * f.x), v = sg * (g[2 * c2 + 1] * f.y);
       op[c2] = Cvt<T>::pack(u, v);
-      atomicAdd(&sacc[2 * c2], u + v);
-      atomicAdd(&sacc[2 * c2 + 1], u * u + v * v);
+      row[2 * c2] = u + v;
+      row[2 * c2 + 1] = u * u + v * v;
     }
+  } else {
+    for (int i = lane; i < C; i += 32) row[i] = 0.f;
   }
   __syncthreads();
   if (stats != nullptr)
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&stats[int64_t(b) * C + i], double(sacc[i]));
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      float t = 0.f;
+      for (int w8 = 0; w8 < 8; ++w8) t += sacc[w8 * C + i];  // fixed order
+      atomicAdd(&stats[int64_t(b) * C + i], static_cast<unsigned long long>(__double2ll_rn(double(t) * kStatScale)));
+    }
 }
 
 // ------------------------------------------------------------------------------------------

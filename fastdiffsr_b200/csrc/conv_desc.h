@@ -48,7 +48,7 @@ struct ConvChunk {
 
 struct ConvSrc {
   const void* ptr;      // NHWC 16-bit
-  const double* stats;  // [B][C/2][2] (sum, sum of squares) per channel pair, or null
+  const unsigned long long* stats;  // [B][C/2][2] fixed-point (sum, sum of squares) per channel pair, or null
   int32_t C;
   int32_t H, W;         // spatial size of the source tensor
 };
@@ -73,7 +73,7 @@ struct ConvLayer {
   int32_t bias_tstride; // floats between steps (0 when the bias does not depend on t)
   const void* resid;    // identity residual, NHWC 16-bit with N channels, or null
   void* out;            // NHWC 16-bit [B][H][W][N]  |  fp32 NCHW [B][out_c][H][W]
-  double* out_stats;    // [B][N/2][2] or null
+  unsigned long long* out_stats;  // [B][N/2][2] fixed point, or null
   int32_t out_mode;     // OutMode
   int32_t out_c;
   const uint8_t* weights;  // packed blobs

@@ -31,6 +31,9 @@ constexpr int kProdThreads = kProdWarps * 32;  // 320
 constexpr int kMaxUnits = 9;                   // ceil(340*8 / 320)
 constexpr int kAStages = 2;
 constexpr int kMaxGnC = 512;
+// GroupNorm statistics are accumulated as 64-bit fixed point (2^-24 resolution): integer atomics
+// are associative, so the sums do not depend on the order in which CTAs finish.
+constexpr double kStatScale = 16777216.0;
 
 template <int N>
 struct ConvCfg {
@@ -49,7 +52,7 @@ struct ConvCfg {
   static constexpr int kOffGstat = kOffTable + kMaxGnC * 8;
   static constexpr int kOffBias = kOffGstat + 64 * 8;
   static constexpr int kOffTstat = kOffBias + 256 * 4;
-  static constexpr int kOffBar = kOffTstat + 256 * 4;
+  static constexpr int kOffBar = kOffTstat + 4 * 256 * 4;  // one row of pair sums per epilogue warp
   static constexpr int kNumBar = 2 * kAStages + 2 * kBStages + 2 * kNumAcc;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16;
@@ -227,7 +230,6 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
     const int et = tid - 128;          // 0..127
     const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride;
     for (int i = et; i < N; i += 128) bias_s[i] = bias_g[i];
-    for (int i = et; i < 256; i += 128) tstat[i] = 0.f;
     named_bar_sync(2, 128);
     const int m = q * 32 + lane, g = m >> 3, r = m & 7;
     const bool do_stats = (L.out_stats != nullptr) && (L.out_mode == kOutAct);
@@ -236,17 +238,21 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
       const int b = tile / tiles_per_img;
       const int rem = tile - b * tiles_per_img;
       const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
+      const int x = tx * kTileW + r;
       mbar_wait(bar_acc_full(acc), accph);
       tc_fence_after();
 #pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
-        const int y = ty * kTileH + mt * 16 + g, x = tx * kTileW + r;
-        const bool valid = y < L.H && x < L.W;
-        const size_t pix = (size_t(b) * L.H + y) * L.W + x;
-        const uint32_t taddr =
-            tmem + (uint32_t(q * 32) << 16) + acc * Cfg::kAccCols + mt * Cfg::kAccStride;
+      for (int cb = 0; cb < Cfg::kNcb; ++cb) {
+        float s[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[j] = 0.f;
 #pragma unroll 1
-        for (int cb = 0; cb < Cfg::kNcb; ++cb) {
+        for (int mt = 0; mt < 2; ++mt) {
+          const int y = ty * kTileH + mt * 16 + g;
+          const bool valid = y < L.H && x < L.W;
+          const size_t pix = (size_t(b) * L.H + y) * L.W + x;
+          const uint32_t taddr =
+              tmem + (uint32_t(q * 32) << 16) + acc * Cfg::kAccCols + mt * Cfg::kAccStride;
           uint32_t raw[32];
           tmem_ld32(taddr + cb * 32, raw);
           tmem_ld_wait();
@@ -281,17 +287,13 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
                 u.w = Cvt<T>::pack(v[k * 8 + 6], v[k * 8 + 7]);
                 op[k] = u;
               }
-            }
-            if (do_stats) {
-              float s[32];
+              if (do_stats) {
 #pragma unroll
-              for (int p = 0; p < 16; ++p) {
-                const float a = valid ? v[2 * p] : 0.f, c2 = valid ? v[2 * p + 1] : 0.f;
-                s[2 * p] = a + c2;
-                s[2 * p + 1] = a * a + c2 * c2;
+                for (int p = 0; p < 16; ++p) {
+                  s[2 * p] += v[2 * p] + v[2 * p + 1];
+                  s[2 * p + 1] = fmaf(v[2 * p], v[2 * p], fmaf(v[2 * p + 1], v[2 * p + 1], s[2 * p + 1]));
+                }
               }
-              const float tot = warp_transpose_reduce32(s, lane);
-              atomicAdd(&tstat[cb * 32 + lane], tot);
             }
           } else {  // fp32 NCHW, first out_c channels (final conv -> eps)
             if (valid && cb == 0) {
@@ -302,16 +304,24 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
             }
           }
         }
+        if (do_stats) {
+          // fixed-order reduction: registers (mt) -> lanes (butterfly) -> this warp's slot row
+          const float tot = warp_transpose_reduce32(s, lane);
+          tstat[q * 256 + cb * 32 + lane] = tot;
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty(acc));
       if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
       if (do_stats) {
+        // warps in fixed order, then order-independent 64-bit fixed-point atomics: the statistics
+        // (and therefore every activation) are bitwise reproducible run to run
         named_bar_sync(2, 128);
         for (int i = et; i < N; i += 128) {
-          atomicAdd(L.out_stats + size_t(b) * N + i, double(tstat[i]));
-          tstat[i] = 0.f;
+          const float tsum = ((tstat[i] + tstat[256 + i]) + tstat[512 + i]) + tstat[768 + i];
+          atomicAdd(L.out_stats + size_t(b) * N + i,
+                    static_cast<unsigned long long>(__double2ll_rn(double(tsum) * kStatScale)));
         }
         named_bar_sync(2, 128);
       }
@@ -341,10 +351,13 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
           for (int pv = pidx * ppg; pv < (pidx + 1) * ppg; ++pv) {
             const int si = pv < p0 ? 0 : 1;
             const int pl = pv < p0 ? pv : pv - p0;
-            const double* st = L.src[si].stats + (size_t(b) * (L.src[si].C >> 1) + pl) * 2;
-            S += st[0];
-            Q += st[1];
+            const long long* st = reinterpret_cast<const long long*>(L.src[si].stats) +
+                                  (size_t(b) * (L.src[si].C >> 1) + pl) * 2;
+            S += double(st[0]);
+            Q += double(st[1]);
           }
+          S *= (1.0 / kStatScale);
+          Q *= (1.0 / kStatScale);
           const double n = double(cpg) * L.src[0].H * L.src[0].W;
           const double mean = S / n;
           double var = Q / n - mean * mean;

@@ -172,6 +172,16 @@ class Engine:
         n = B * c.value * h.value * w.value
         return buf[:n].view(B, c.value, h.value, w.value)
 
+    def profile_unet(self, t: int, reps: int = 3):
+        """[(op name, mean ms, algorithmic conv FLOPs)] for one UNet evaluation at the current shape."""
+        n = self.lib.fdsr_debug_num_ops(self._h)
+        ms = (C.c_float * n)()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_debug_profile_unet(self._h, t, reps, ms, n, self._stream()),
+                        "fdsr_debug_profile_unet")
+        return [(self.lib.fdsr_debug_op_name(self._h, i).decode(), float(ms[i]),
+                 float(self.lib.fdsr_debug_op_flops(self._h, i))) for i in range(n)]
+
     def launch_count(self):
         return int(self.lib.fdsr_launch_count(self._h))
 

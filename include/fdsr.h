@@ -129,6 +129,16 @@ const char* fdsr_debug_tensor_name(const fdsr_ctx* ctx, int32_t i);
 /* Converts activation tensor `name` of the last fdsr_unet_forward (NHWC 16-bit) to fp32 NCHW. */
 int fdsr_debug_read_tensor(fdsr_ctx* ctx, const char* name, float* out_dev, int64_t capacity,
                            int32_t* C, int32_t* H, int32_t* W, void* stream);
+/* Per-op profiling of one UNet evaluation on the context's current buffers (call after a forward
+ * or sample at the shape of interest): runs the ops `reps` times with a CUDA-event pair around
+ * each op's launch(es) on `stream`, writes the mean milliseconds per op to ms_out_host and returns
+ * the number of ops.  Synchronous.  Op names / algorithmic conv FLOPs (at the reserved shape) for
+ * turning the times into TFLOP/s: */
+int32_t fdsr_debug_num_ops(const fdsr_ctx* ctx);
+const char* fdsr_debug_op_name(const fdsr_ctx* ctx, int32_t i);
+double fdsr_debug_op_flops(const fdsr_ctx* ctx, int32_t i);
+int fdsr_debug_profile_unet(fdsr_ctx* ctx, int32_t t, int32_t reps, float* ms_out_host, int32_t cap,
+                            void* stream);
 /* Kernel launches enqueued by this context so far (library kernels only). */
 int64_t fdsr_launch_count(const fdsr_ctx* ctx);
 /* Algorithmic conv FLOPs (2*MAC, padding counted) of one UNet forward at the reserved shape. */

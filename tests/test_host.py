@@ -1,0 +1,118 @@
+"""Host-side logic of the drop-in boundary: config loading, define_G surface, state_dict
+compatibility, schedule buffers, loud failure without a GPU, C-ABI exports.  CPU only."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import fastdiffsr_b200 as F
+from fastdiffsr_b200 import _lib
+from fastdiffsr_b200.config import default_config, load_config, NoneDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = "/root/reference/FastDiffSR/config"
+
+
+def test_config_comment_stripping(tmp_path):
+    p = tmp_path / "c.json"
+    p.write_text('{\n "phase": "val", // train or val\n "gpu_ids": [0, 1],\n // whole line\n "model": {"x": 1}\n}\n')
+    opt = load_config(str(p), phase="val")
+    assert opt["gpu_ids"] == [0, 1] and opt["distributed"] is True
+    assert isinstance(opt["model"], NoneDict) and opt["model"]["missing"] is None
+
+
+def test_default_configs_cover_reference_names():
+    for name in ("sr_fastdiffsr_test_64_256", "sr_fastdiffsr_test_32_256", "sr_fastdiffsr_infer_x4",
+                 "sr_fastdiffsr_infer_128_512.json"):
+        opt = default_config(name)
+        assert opt["model"]["which_model_G"] == "fastdiffsr"
+        assert opt["model"]["beta_schedule"]["val"]["n_timestep"] == 20
+    assert default_config("sr_fastdiffsr_infer_x4")["datasets"]["val"]["r_resolution"] == 512
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference tree only exists in the build container")
+def test_default_configs_equal_reference_json():
+    for name in ("sr_fastdiffsr_test_64_256", "sr_fastdiffsr_test_32_256", "sr_fastdiffsr_infer_x4"):
+        ref = load_config(os.path.join(REF_CFG, name + ".json"))
+        mine = default_config(name)
+        for key in ("unet", "beta_schedule", "diffusion", "which_model_G"):
+            assert ref["model"][key] == mine["model"][key], (name, key)
+        assert ref["datasets"]["train"]["l_resolution"] == mine["datasets"]["train"]["l_resolution"]
+    # README names a file that does not exist; the alias resolves to infer_x4
+    opt = load_config(os.path.join(REF_CFG, "sr_fastdiffsr_infer_128_512.json"))
+    assert opt["datasets"]["val"]["l_resolution"] == 128
+
+
+def test_define_G_surface_and_state_dict(oracle, golden_dir):
+    opt = default_config()
+    netG = F.define_G(opt)
+    assert isinstance(netG, torch.nn.Module) and netG.conditional and netG.channels == 3 and netG.image_size == 256
+    keys = [(k, tuple(v.shape)) for k, v in netG.state_dict().items()]
+    spec = [(k, s) for k, s, _, _ in oracle.state_dict_spec(oracle.DEFAULT_UNET)]
+    assert keys == spec
+    netG.set_loss("cpu")
+    netG.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], "cpu")
+    assert netG.num_timesteps == 20 and netG.betas.device.type == "cpu"
+    g = np.load(os.path.join(golden_dir, "schedule_T20.npz"))
+    for k in g.files:
+        if k == "sqrt_alphas_cumprod_prev":
+            assert np.array_equal(netG.sqrt_alphas_cumprod_prev, g[k])
+        else:
+            assert np.array_equal(getattr(netG, k).numpy(), g[k]), k
+    assert len(netG.state_dict()) == 317 + 12
+    # a reference-style checkpoint (weights + the 12 buffers) loads strictly
+    sd = oracle.make_state_dict(oracle.DEFAULT_UNET, seed=3)
+    for k in g.files:
+        if k != "sqrt_alphas_cumprod_prev":
+            sd[k] = torch.from_numpy(g[k])
+    netG.load_state_dict(sd, strict=True)
+    assert torch.equal(netG.denoise_fn.downs[0].weight, sd["denoise_fn.downs.0.weight"])
+    netG.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], "cpu")  # re-entrant like the reference
+
+
+def test_other_generators_and_training_rejected():
+    opt = default_config()
+    opt["model"]["which_model_G"] = "ddpm"
+    with pytest.raises(NotImplementedError):
+        F.define_G(opt)
+    with pytest.raises(NotImplementedError):
+        F.define_G(default_config(phase="train"))
+    with pytest.raises(NotImplementedError):
+        F.make_beta_schedule("nope", 20)
+
+
+def test_no_cpu_fallback():
+    opt = default_config()
+    netG = F.define_G(opt)
+    netG.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], "cpu")
+    with pytest.raises(F.FdsrError):
+        netG.super_resolution(torch.zeros(1, 3, 64, 64), False)
+    with pytest.raises(NotImplementedError):
+        netG({"HR": None, "SR": None})
+
+
+def test_beta_schedules_match_oracle(oracle):
+    for name in ("linear", "quad", "const", "jsd", "warmup10", "warmup50", "linear_cosine"):
+        a = F.make_beta_schedule(name, 20, 1e-6, 1e-2)
+        assert np.array_equal(a, oracle.make_beta_schedule(name, 20, 1e-6, 1e-2)), name
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fdsr.h")).read()
+    declared = sorted(set(re.findall(r"\b(fdsr_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    assert os.path.exists(_lib.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert sorted(_lib.EXPORTS) == declared  # the Python binding covers exactly the header
+    # error path that needs no GPU: creating a context without a device fails loudly
+    if not torch.cuda.is_available():
+        cfg = _lib.FdsrConfig()
+        h = ctypes.c_void_p()
+        l = _lib.load()
+        assert l.fdsr_create(ctypes.byref(cfg), ctypes.byref(h)) < 0
+        assert b"no CPU fallback" in l.fdsr_global_error() or b"CUDA" in l.fdsr_global_error()
