@@ -195,10 +195,12 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps, eng.launch_count() - l0
 
+    ws_gib = None
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
     ms_dev, launches = timed(step_device, args.steps, max(args.warmup, 3))
+    ws_gib = eng.workspace_bytes() / 2 ** 30
     ms_e2e, _ = timed(step_host, max(2, min(args.steps, 5)), 1)
     clk = clocks.stop() if clocks else None
     value = B * world / (ms_dev / 1e3)
@@ -248,7 +250,7 @@ def run_ours(args, rank, world, local_rank):
                                       f"FastDiffSR x{H // h} {h}->{H} T={T} sampling, batch {B}/GPU",
                           "global_batch": B * world, "parallelism": f"image-sharded x{world}",
                           "l2": "working set per step (activations %.1f GiB) exceeds the 126 MB L2; no flush needed"
-                                % (eng.workspace_bytes() / 2 ** 30),
+                                % ws_gib,
                           "ms_per_unet_step": ms_dev / T, "noise": "on-device Philox (value), same (e2e)"},
                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(lr_host.nbytes),
                        "d2h_bytes_per_step": int(B * 3 * H * H * 4), "ms_per_step": ms_e2e,

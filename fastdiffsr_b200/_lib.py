@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfdsr.so")
+LIB_PATH = os.environ.get("FDSR_LIB", os.path.join(_HERE, "libfdsr.so"))
 CSRC = os.path.join(_HERE, "csrc")
 MAX_LEVELS = 8
 DTYPE_FP16, DTYPE_BF16 = 0, 1
@@ -77,6 +77,8 @@ _SIGS = {
     "fdsr_debug_op_flops": (C.c_double, [C.c_void_p, C.c_int32]),
     "fdsr_debug_profile_unet": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32,
                                           C.c_void_p]),
+    "fdsr_debug_role_cycles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int32,
+                                         C.c_void_p]),
     "fdsr_launch_count": (C.c_int64, [C.c_void_p]),
     "fdsr_unet_flops": (C.c_double, [C.c_void_p]),
     "fdsr_set_use_graph": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -94,7 +95,8 @@ struct fdsr_ctx {
   size_t stats_off = 0, stats_bytes = 0;
   size_t off_cond = 0, off_x = 0, off_eps = 0, off_sr = 0, off_psum = 0, off_pmax = 0, off_gate = 0,
          off_sp = 0, off_seed = 0;
-  ConvLayer* d_layers = nullptr;
+  std::vector<ConvLayer> h_layers;  // passed by value as __grid_constant__ kernel parameters
+  long long* d_prof = nullptr;  // role cycle counters (FDSR_PROFILE builds)
   bool layers_dirty = true;
   // bicubic tables (cached per size pair)
   struct BicTab {
@@ -111,6 +113,7 @@ struct fdsr_ctx {
   size_t d_stage_bytes = 0;
   // graph cache
   bool use_graph = true;
+  bool precise = false;  // FDSR_PRECISE_SWISH=1: fp32 Swish in the producers
   cudaGraphExec_t graph = nullptr;
   struct {
     int B = 0, H = 0, W = 0;
@@ -520,6 +523,10 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int upload_layers(fdsr_ctx* c) {
   const int B = c->B, H = c->H, W = c->W;
+  if (!c->d_prof) {
+    CUDA_TRY(c, cudaMalloc(&c->d_prof, size_t(c->num_sms) * 32 * 8));
+    CUDA_TRY(c, cudaMemset(c->d_prof, 0, size_t(c->num_sms) * 32 * 8));
+  }
   std::vector<ConvLayer> L(c->convs.size());
   for (size_t i = 0; i < c->convs.size(); ++i) {
     const HConv& k = c->convs[i];
@@ -559,6 +566,7 @@ int upload_layers(fdsr_ctx* c) {
     l.gn_nsrc = k.gn_nsrc;
     l.gn_groups = c->cfg.norm_groups;
     l.gn_eps = 1e-5f;
+    l.precise = c->precise ? 1 : 0;
     if (k.gn_C) {
       l.gamma = c->d_params + k.gamma_off;
       l.beta = c->d_params + k.gamma_off + k.gn_C;
@@ -579,17 +587,27 @@ int upload_layers(fdsr_ctx* c) {
     l.tiles_x = (l.W + kTileW - 1) / kTileW;
     l.tiles_y = (l.H + kTileH - 1) / kTileH;
     l.ntiles = B * l.tiles_x * l.tiles_y;
+    {
+      const int tpi = l.tiles_x * l.tiles_y;
+      // running TMEM statistics exist for N = 64 only; the group size must not depend on B
+      l.group = (k.N == 64 && tpi % 2 == 0) ? 2 : 1;
+    }
+    l.prof = c->d_prof;
   }
-  if (!c->d_layers) CUDA_TRY(c, cudaMalloc(&c->d_layers, L.size() * sizeof(ConvLayer)));
-  CUDA_TRY(c, cudaMemcpy(c->d_layers, L.data(), L.size() * sizeof(ConvLayer), cudaMemcpyHostToDevice));
+  static_assert(sizeof(ConvLayer) <= 4000, "ConvLayer must fit the kernel parameter space");
+  c->h_layers = L;
   c->layers_dirty = false;
   return FDSR_OK;
 }
 
 template <int N, typename T>
 cudaError_t set_conv_attr() {
-  return cudaFuncSetAttribute(conv_gemm_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              ConvCfg<N>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ConvCfg<N>::kSmemBytes);
+  if (e == cudaSuccess && Cvt<T>::kFmt == 0)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, Cvt<T>::kFmt == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ConvCfg<N>::kSmemBytes);
+  return e;
 }
 template <typename T>
 cudaError_t set_conv_attrs() {
@@ -602,8 +620,12 @@ cudaError_t set_conv_attrs() {
 
 template <int N, typename T>
 int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
-  const int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
-  conv_gemm_kernel<N, T><<<grid, kConvThreads, ConvCfg<N>::kSmemBytes, st>>>(c->d_layers + li, t);
+  const int ngroups = ntiles / c->h_layers[li].group;
+  const int grid = ngroups < c->num_sms ? ngroups : c->num_sms;
+  if (Cvt<T>::kFmt == 0 && !c->precise)
+    conv_gemm_kernel<N, T, Cvt<T>::kFmt == 0><<<grid, kConvThreads, ConvCfg<N>::kSmemBytes, st>>>(c->h_layers[li], t);
+  else
+    conv_gemm_kernel<N, T, false><<<grid, kConvThreads, ConvCfg<N>::kSmemBytes, st>>>(c->h_layers[li], t);
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
   return FDSR_OK;
@@ -806,6 +828,10 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     return fail(nullptr, FDSR_E_CUDA, "libfdsr needs an sm_100 (B200) device");
   }
   c->num_sms = prop.multiProcessorCount;
+  {
+    const char* e = getenv("FDSR_PRECISE_SWISH");
+    c->precise = e && e[0] == '1';
+  }
   if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
     delete c;
     return fail(nullptr, FDSR_E_INVALID, "dtype must be FDSR_DTYPE_FP16 or FDSR_DTYPE_BF16");
@@ -833,7 +859,7 @@ int fdsr_destroy(fdsr_ctx* c) {
   cudaFree(c->d_params);
   cudaFree(c->d_bias);
   cudaFree(c->d_ws);
-  cudaFree(c->d_layers);
+  cudaFree(c->d_prof);
   cudaFree(c->d_bic_tmp);
   cudaFree(c->d_stage);
   if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -1252,6 +1278,28 @@ int fdsr_debug_profile_unet(fdsr_ctx* c, int32_t t, int32_t reps, float* ms_out_
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return nops;
+}
+
+int fdsr_debug_role_cycles(fdsr_ctx* c, int32_t op, int32_t t, int64_t* out_host, int32_t cap, void* stream) {
+  if (!c || !out_host) return fail(c, FDSR_E_INVALID, "null argument");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!c->d_ws) return fail(c, FDSR_E_STATE, "run a forward first");
+  if (op < 0 || op >= int(c->ops.size()) || c->ops[op].kind != 0) return fail(c, FDSR_E_INVALID, "op is not a conv");
+  const int n = c->num_sms * 32;
+  if (cap < n) return fail(c, FDSR_E_INVALID, "capacity too small");
+  if (c->layers_dirty) {
+    rc = upload_layers(c);
+    if (rc) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(c, cudaMemsetAsync(c->d_prof, 0, size_t(n) * 8, st));
+  rc = c->cfg.dtype == FDSR_DTYPE_BF16 ? launch_conv<__nv_bfloat16>(c, c->ops[op].idx, t, st)
+                                        : launch_conv<__half>(c, c->ops[op].idx, t, st);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemcpyAsync(out_host, c->d_prof, size_t(n) * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  return n;
 }
 
 int64_t fdsr_launch_count(const fdsr_ctx* c) { return c ? c->launches : 0; }

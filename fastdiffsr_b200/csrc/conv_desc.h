@@ -68,6 +68,7 @@ struct ConvLayer {
   const float* gamma;   // [gn_C]
   const float* beta;    // [gn_C]
   float gn_eps;
+  int32_t precise;      // 1: fp32 EX2/RCP Swish (always for bf16); 0: packed-half tanh Swish (fp16)
   // epilogue
   const float* bias;    // [T or 1][N] fp32: conv bias (+ residual-conv bias) (+ FiLM vector of step t)
   int32_t bias_tstride; // floats between steps (0 when the bias does not depend on t)
@@ -78,6 +79,8 @@ struct ConvLayer {
   int32_t out_c;
   const uint8_t* weights;  // packed blobs
   int32_t tiles_x, tiles_y, ntiles;
+  int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)
+  long long* prof;         // role cycle counters [grid][4 roles][8 slots] (FDSR_PROFILE builds only)
 };
 
 }  // namespace fdsr

@@ -4,17 +4,24 @@
 //   M = 256 output pixels per CTA tile (32x8 pixels = two 128-row MMA tiles), N = all output
 //   channels (16/64/128/256), K = taps x input channels, walked in chunks of 64 channels.
 //
-// Warp roles (512 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0      MMA issuer (one thread): tcgen05.mma from shared-memory descriptors
-//   warp 1      weight loader (one thread): cp.async.bulk of pre-packed per-tap blobs
-//   warps 4-7   epilogue: tcgen05.ld -> bias/FiLM -> residual -> GroupNorm pair statistics -> store
-//   warps 2,3,8-15  input producers: coalesced 16B global loads of the (32+2)x(8+2) input patch,
-//               GroupNorm scale/shift + Swish in fp32 registers, 16B stores into the resident
+// Warp roles (640 threads, 1 CTA / SM, persistent over a contiguous range of tiles):
+//   warp 0      MMA issuer (one elected thread): tcgen05.mma from shared-memory descriptors
+//   warp 1      weight loader (one elected thread): cp.async.bulk of pre-packed tap blobs
+//   warps 4-11  epilogue (one warpgroup per 128-row MMA tile): tcgen05.ld -> bias/FiLM -> residual
+//               -> 16-bit store -> GroupNorm pair statistics
+//   warps 2,3,12-19  input producers: coalesced 16B global loads of the (32+2)x(8+2) input patch,
+//               GroupNorm scale/shift + Swish in registers, 16B stores into the resident
 //               patch laid out as [channel group][position][8 ch] (no-swizzle core matrices).
 // The patch is loaded and transformed ONCE per 64-channel chunk and then serves all nine 3x3
 // taps as shifted shared-memory descriptor views (start address + 16 B * (dy*10 + dx), SBO =
 // 160 B), so the A operand is never re-fetched per tap and GroupNorm/Swish/concat/upsample/
 // space-to-depth never touch HBM as separate passes.
+//
+// The kernel is instruction-issue sensitive (ncu: ~0.35 IPC per scheduler with 5 warps each), so
+// the layer description is a __grid_constant__ kernel parameter (constant-bank operands instead of
+// shared-memory loads), per-thread patch coordinates are computed once per launch, waits use the
+// mbarrier suspend hint instead of spinning, and for N = 64 the GroupNorm statistics are kept as
+// per-lane running sums in spare TMEM columns and reduced across lanes only when the sample changes.
 //
 // Reference ops covered (FastDiffSR/model/fastdiffsr_modules/unet.py): Block :89-101 (GroupNorm,
 // Swish, Conv3x3), ResnetBlock :104-120 (FiLM add, residual 1x1 / identity), Downsample :77-83,
@@ -25,10 +32,12 @@
 
 namespace fdsr {
 
-constexpr int kConvThreads = 512;
+constexpr int kConvThreads = 640;              // 20 warps (register file: 96 regs/thread)
 constexpr int kProdWarps = 10;
 constexpr int kProdThreads = kProdWarps * 32;  // 320
 constexpr int kMaxUnits = 9;                   // ceil(340*8 / 320)
+constexpr int kEpiWarps = 8;                   // warps 4..11: (warp % 4) = TMEM lane quarter, (warp-4)/4 = MMA tile
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kAStages = 2;
 constexpr int kMaxGnC = 512;
 // GroupNorm statistics are accumulated as 64-bit fixed point (2^-24 resolution): integer atomics
@@ -40,19 +49,25 @@ struct ConvCfg {
   static constexpr int kAccStride = N < 32 ? 32 : N;        // TMEM columns per 128-row accumulator
   static constexpr int kAccCols = 2 * kAccStride;           // two MMA tiles per CTA tile
   static constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;
-  static constexpr int kTmemCols = kNumAcc * kAccCols < 32 ? 32 : kNumAcc * kAccCols;
-  static constexpr int kBStageBytes = N * 128;
-  static constexpr int kBStages = N >= 256 ? 4 : (N >= 128 ? 6 : 8);
+  // N = 64: per-lane running GroupNorm sums live in TMEM columns [256, 384)
+  static constexpr bool kStatsInTmem = (N == 64);
+  static constexpr int kStatCol0 = kNumAcc * kAccCols;
+  static constexpr int kTmemNeed = kNumAcc * kAccCols + (kStatsInTmem ? 2 * N : 0);
+  static constexpr int kTmemCols =
+      kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
+  // a B stage holds as many consecutive tap blobs of one chunk as fit (N=64: 4 taps, 128: 2, 256: 1)
+  static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : 32768;
+  static constexpr int kBStages = N >= 256 ? 3 : (N < 32 ? 2 : 4);
   static constexpr int kNcb = N < 32 ? 1 : N / 32;
+  static constexpr int kRow = N < 32 ? 32 : N;  // floats per epilogue-warp statistics row
   // shared memory carve-up (bytes)
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + kAStages * kAStageBytes;
-  static constexpr int kOffLayer = kOffB + kBStages * kBStageBytes;
-  static constexpr int kOffTable = kOffLayer + ((int(sizeof(ConvLayer)) + 15) / 16) * 16;
+  static constexpr int kOffTable = kOffB + kBStages * kBStageBytes;
   static constexpr int kOffGstat = kOffTable + kMaxGnC * 8;
   static constexpr int kOffBias = kOffGstat + 64 * 8;
   static constexpr int kOffTstat = kOffBias + 256 * 4;
-  static constexpr int kOffBar = kOffTstat + 4 * 256 * 4;  // one row of pair sums per epilogue warp
+  static constexpr int kOffBar = kOffTstat + kEpiWarps * kRow * 4;  // one row of pair sums per epilogue warp
   static constexpr int kNumBar = 2 * kAStages + 2 * kBStages + 2 * kNumAcc;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   static constexpr int kSmemBytes = kOffTmem + 16;
@@ -85,8 +100,41 @@ struct Cvt<__nv_bfloat16> {
 
 __device__ __forceinline__ float swish_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
 
+// swish(x*2sc + 2sh) for a packed pair, with sc/sh pre-halved: h = x*sc + sh; h*tanh(h) + h
+__device__ __forceinline__ uint32_t swish_h2(uint32_t x, uint32_t sc, uint32_t sh) {
+  uint32_t h, t, o;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(x), "r"(sc), "r"(sh));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
+  return o;
+}
+
+// true in exactly one lane of a fully converged warp (elect.sync keeps the uniform datapath usable)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 16-byte read-only global load, zero when !pred (no branch)
+__device__ __forceinline__ uint4 ldg16_pred(const void* p, bool pred) {
+  uint4 v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\tmov.u32 %3, 0;\n\t"
+      "@q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p), "r"(int(pred)));
+  return v;
 }
 
 // Sum v[j] over the 32 lanes of a warp for all 32 j at once; lane l returns the total of v[l].
@@ -104,20 +152,35 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
-template <int N, typename T>
+// Optional role-level cycle accounting (tools/ only; compiled in with -DFDSR_PROFILE).
+#ifdef FDSR_PROFILE
+#define PROF_DECL long long pt_ = clock64(), pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(slot)              \
+  do {                               \
+    const long long n_ = clock64();  \
+    pacc_[slot] += n_ - pt_;         \
+    pt_ = n_;                        \
+  } while (0)
+#define PROF_FLUSH(role)                                                                  \
+  do {                                                                                    \
+    if (L.prof != nullptr)                                                                \
+      for (int k_ = 0; k_ < 8; ++k_) L.prof[(size_t(blockIdx.x) * 4 + (role)) * 8 + k_] = pacc_[k_]; \
+  } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(slot)
+#define PROF_FLUSH(role)
+#endif
+
+// kFast: GroupNorm-affine + Swish in packed fp16 (tanh form); otherwise fp32 EX2/RCP.
+template <int N, typename T, bool kFast>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
+conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   using Cfg = ConvCfg<N>;
+  constexpr int kRow = Cfg::kRow;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- stage the layer description in shared memory
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(layer_g);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + Cfg::kOffLayer);
-    for (int i = tid; i < int(sizeof(ConvLayer) / 4); i += kConvThreads) dst[i] = src[i];
-  }
-  const ConvLayer& L = *reinterpret_cast<const ConvLayer*>(smem + Cfg::kOffLayer);
   float2* table = reinterpret_cast<float2*>(smem + Cfg::kOffTable);
   float2* gstat = reinterpret_cast<float2*>(smem + Cfg::kOffGstat);
   float* bias_s = reinterpret_cast<float*>(smem + Cfg::kOffBias);
@@ -144,7 +207,7 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
     }
     for (int s = 0; s < Cfg::kNumAcc; ++s) {
       mbar_init(bar_acc_full(s), 1);
-      mbar_init(bar_acc_empty(s), 4);
+      mbar_init(bar_acc_empty(s), kEpiWarps);
     }
     mbar_init_fence();
   }
@@ -154,190 +217,315 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int ntiles = L.ntiles;
+  // contiguous, balanced range of tiles for this CTA: consecutive tiles share the sample (GroupNorm
+  // table stays valid) and their halos (L2 locality).
+  // The unit of assignment is a group of L.group consecutive tiles of one image: running statistics
+  // are reduced per group, so every partial sum is computed identically whatever the batch size or
+  // the position of the image in the batch (results are bitwise independent of how a batch is sharded).
+  const int tgroup = L.group;
+  const int ngroups = L.ntiles / tgroup;
+  const int tq = ngroups / int(gridDim.x), tr = ngroups - tq * int(gridDim.x);
+  const int group_begin = int(blockIdx.x) * tq + (int(blockIdx.x) < tr ? int(blockIdx.x) : tr);
+  const int tile_begin = group_begin * tgroup;
+  const int tile_end = (group_begin + tq + (int(blockIdx.x) < tr ? 1 : 0)) * tgroup;
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int ncg = L.ncg;
+  const uint32_t blob = uint32_t(ncg) * N * 16;  // bytes of one tap's weight blob
+  const int taps_per_stage =
+      int(Cfg::kBStageBytes / blob) < kMaxTaps ? int(Cfg::kBStageBytes / blob) : kMaxTaps;
   const uint32_t sA = smem_u32(smem + Cfg::kOffA);
   const uint32_t sB = smem_u32(smem + Cfg::kOffB);
 
   if (warp == 0) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, N, Cvt<T>::kFmt);
-      // descriptor high words are constant; low words get the start address added
-      const uint32_t a_hi = ((kPatchW * 16) >> 4) | (1u << 14);
-      const uint32_t a_lo0 = (uint32_t(kPlaneBytes >> 4) << 16);
-      const uint32_t b_hi = (128u >> 4) | (1u << 14);
-      const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16);
-      const int ksteps = ncg >> 1;
-      int as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(bar_acc_empty(acc), accph ^ 1);
-        tc_fence_after();
-        const uint32_t d0 = tmem + acc * Cfg::kAccCols;
-        for (int c = 0; c < L.nchunks; ++c) {
-          const ConvChunk& ck = L.chunk[c];
-          mbar_wait(bar_a_full(as), aph);
+    // =========================================================== MMA issuer (whole warp converged,
+    // tcgen05 instructions issued by the elected lane)
+    const uint32_t idesc = make_idesc_f16(128, N, Cvt<T>::kFmt);
+    // descriptor = hi:lo; hi is constant, lo = (LBO>>4)<<16 | (addr>>4), advanced by plain adds
+    const uint32_t a_hi = ((kPatchW * 16) >> 4) | (1u << 14);
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo0 = (uint32_t(kPlaneBytes >> 4) << 16) + (sA >> 4);
+    const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16) + (sB >> 4);
+    const int ksteps = ncg >> 1;
+    int as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
+    PROF_DECL;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(bar_acc_empty(acc), accph ^ 1);
+      PROF_MARK(0);
+      tc_fence_after();
+      const uint32_t d0 = tmem + acc * Cfg::kAccCols;
+      for (int c = 0; c < L.nchunks; ++c) {
+        const ConvChunk& ck = L.chunk[c];
+        const int ntaps = ck.ntaps;
+        mbar_wait(bar_a_full(as), aph);
+        PROF_MARK(1);
+        const uint32_t a_stage = a_lo0 + as * (kAStageBytes >> 4);
+        for (int tp0 = 0; tp0 < ntaps; tp0 += taps_per_stage) {
+          const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
+          mbar_wait(bar_b_full(bs), bph);
+          PROF_MARK(2);
           tc_fence_after();
-          const uint32_t a_base = (sA + as * kAStageBytes) >> 4;
-          for (int tp = 0; tp < ck.ntaps; ++tp) {
-            mbar_wait(bar_b_full(bs), bph);
-            tc_fence_after();
-            const uint32_t b_base = (sB + bs * Cfg::kBStageBytes) >> 4;
-            const uint32_t a_tap = a_base + ck.tap_pos[tp];
-            const uint32_t first = (c | tp) == 0 ? 0u : 1u;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t bd =
-                  (uint64_t(b_hi) << 32) | (b_lo0 | (b_base + ks * 2 * N));
-              const uint32_t a_k = a_tap + ks * 2 * kPlanePos;
-              const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo0 | a_k);
-              const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo0 | (a_k + 16 * kPatchW));
-              const uint32_t accum = first | (ks ? 1u : 0u);
-              umma_f16(d0, ad0, bd, idesc, accum);
-              umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, accum);
+          if (elect_one()) {
+            uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4);
+            for (int tg = 0; tg < g; ++tg, b_lo += blob >> 4) {
+              const uint32_t a_lo = a_stage + ck.tap_pos[tp0 + tg];
+              const uint32_t accum0 = (c | tp0 | tg) == 0 ? 0u : 1u;
+              if (ksteps == 4) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t bd = (uint64_t(b_hi) << 32) | (b_lo + ks * 2 * N);
+                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos);
+                  const uint64_t ad1 =
+                      (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos + 16 * kPatchW);
+                  umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
+                  umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
+                }
+              } else {
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint64_t bd = (uint64_t(b_hi) << 32) | (b_lo + ks * 2 * N);
+                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos);
+                  const uint64_t ad1 =
+                      (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos + 16 * kPatchW);
+                  umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
+                  umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
+                }
+              }
             }
             umma_commit(bar_b_empty(bs));
-            if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+            if (tp0 + g >= ntaps) umma_commit(bar_a_empty(as));
+            if (tp0 + g >= ntaps && c == L.nchunks - 1) umma_commit(bar_acc_full(acc));
           }
-          umma_commit(bar_a_empty(as));
-          if (++as == kAStages) { as = 0; aph ^= 1; }
+          __syncwarp();
+          PROF_MARK(3);
+          if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
         }
-        umma_commit(bar_acc_full(acc));
-        if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
+        if (++as == kAStages) { as = 0; aph ^= 1; }
       }
+      if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
     }
+    if (lane == 0) PROF_FLUSH(0);
   } else if (warp == 1) {
     // =========================================================== weight loader
-    if (lane == 0) {
-      const uint32_t blob = uint32_t(ncg) * N * 16;
-      int bs = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int c = 0; c < L.nchunks; ++c) {
-          const ConvChunk& ck = L.chunk[c];
-          const uint8_t* w = L.weights + ck.w_off;
-          for (int tp = 0; tp < ck.ntaps; ++tp) {
-            mbar_wait(bar_b_empty(bs), bph ^ 1);
-            mbar_arrive_expect_tx(bar_b_full(bs), blob);
-            bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(tp) * blob, blob, bar_b_full(bs));
-            if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+    int bs = 0, bph = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int c = 0; c < L.nchunks; ++c) {
+        const ConvChunk& ck = L.chunk[c];
+        const uint8_t* w = L.weights + ck.w_off;
+        const int ntaps = ck.ntaps;
+        for (int tp0 = 0; tp0 < ntaps; tp0 += taps_per_stage) {
+          const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
+          mbar_wait(bar_b_empty(bs), bph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_b_full(bs), uint32_t(g) * blob);
+            bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(tp0) * blob, uint32_t(g) * blob,
+                     bar_b_full(bs));
           }
+          __syncwarp();
+          if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // =========================================================== epilogue
-    const int q = warp - 4;            // TMEM lane quarter owned by this warp (== warp % 4)
-    const int et = tid - 128;          // 0..127
+    const int ew = warp - 4;           // 0..7
+    const int q = ew & 3;              // TMEM lane quarter owned by this warp (== warp % 4)
+    const int mt = ew >> 2;            // which 128-row MMA tile of the CTA tile
+    const int et = tid - 128;          // 0..255
     const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride;
-    for (int i = et; i < N; i += 128) bias_s[i] = bias_g[i];
-    named_bar_sync(2, 128);
+    for (int i = et; i < kRow; i += kEpiThreads) bias_s[i] = i < N ? bias_g[i] : 0.f;
+    named_bar_sync(2, kEpiThreads);
     const int m = q * 32 + lane, g = m >> 3, r = m & 7;
-    const bool do_stats = (L.out_stats != nullptr) && (L.out_mode == kOutAct);
+    const bool act = L.out_mode == kOutAct;
+    const bool do_stats = (L.out_stats != nullptr) && act;
+    const bool has_res = (L.resid != nullptr) && act;
+    const int H = L.H, W = L.W, tiles_x = L.tiles_x;
+    const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
+    const uint32_t run_addr = lane_base + Cfg::kStatCol0 + mt * N;  // running sums (kStatsInTmem)
+    if (Cfg::kStatsInTmem && do_stats) {
+      uint32_t z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0u;
+      for (int cb = 0; cb < Cfg::kNcb; ++cb) tmem_st32(run_addr + cb * 32, z);
+      tmem_st_wait();
+    }
     int acc = 0, accph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_img;
-      const int rem = tile - b * tiles_per_img;
-      const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
-      const int x = tx * kTileW + r;
+    int b = tile_begin / tiles_per_img;
+    int rem = tile_begin - b * tiles_per_img;
+    int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    PROF_DECL;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int x = tx * kTileW + r, y = ty * kTileH + mt * 16 + g;
+      const bool valid = y < H && x < W;
+      const bool all_valid = __all_sync(0xffffffffu, valid);
+      const size_t pix = (size_t(b) * H + y) * W + x;
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(L.resid) + pix * N);
+      uint4 rq[4];  // identity residual of the next 32 channels, fetched before it is needed
+      if (has_res) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + k, valid);
+      }
       mbar_wait(bar_acc_full(acc), accph);
+      PROF_MARK(0);
       tc_fence_after();
+      const uint32_t taddr = lane_base + acc * Cfg::kAccCols + mt * Cfg::kAccStride;
 #pragma unroll 1
       for (int cb = 0; cb < Cfg::kNcb; ++cb) {
-        float s[32];
+        uint32_t raw[32];
+        tmem_ld32(taddr + cb * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + cb * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s[j] = 0.f;
-#pragma unroll 1
-        for (int mt = 0; mt < 2; ++mt) {
-          const int y = ty * kTileH + mt * 16 + g;
-          const bool valid = y < L.H && x < L.W;
-          const size_t pix = (size_t(b) * L.H + y) * L.W + x;
-          const uint32_t taddr =
-              tmem + (uint32_t(q * 32) << 16) + acc * Cfg::kAccCols + mt * Cfg::kAccStride;
-          uint32_t raw[32];
-          tmem_ld32(taddr + cb * 32, raw);
-          tmem_ld_wait();
-          float v[32];
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + bb.x;
+          v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + bb.y;
+          v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + bb.z;
+          v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + bb.w;
+        }
+        if (act) {
+          if (has_res) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = __uint_as_float(raw[j]) + ((N >= 32 || j < N) ? bias_s[(cb * 32 + j) & 255] : 0.f);
-          if (L.out_mode == kOutAct) {
-            if (L.resid != nullptr && valid) {
-              const uint4* rp = reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const T*>(L.resid) + pix * N + cb * 32);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t w4[4] = {rq[k].x, rq[k].y, rq[k].z, rq[k].w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint4 u = rp[k];
-                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = Cvt<T>::unpack(w4[e]);
-                  v[k * 8 + e * 2] += f.x;
-                  v[k * 8 + e * 2 + 1] += f.y;
-                }
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = Cvt<T>::unpack(w4[e]);
+                v[k * 8 + e * 2] += f.x;
+                v[k * 8 + e * 2 + 1] += f.y;
               }
             }
-            if (valid) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.out) + pix * N + cb * 32);
+            if (cb + 1 < Cfg::kNcb) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                uint4 u;
-                u.x = Cvt<T>::pack(v[k * 8 + 0], v[k * 8 + 1]);
-                u.y = Cvt<T>::pack(v[k * 8 + 2], v[k * 8 + 3]);
-                u.z = Cvt<T>::pack(v[k * 8 + 4], v[k * 8 + 5]);
-                u.w = Cvt<T>::pack(v[k * 8 + 6], v[k * 8 + 7]);
-                op[k] = u;
-              }
-              if (do_stats) {
-#pragma unroll
-                for (int p = 0; p < 16; ++p) {
-                  s[2 * p] += v[2 * p] + v[2 * p + 1];
-                  s[2 * p + 1] = fmaf(v[2 * p], v[2 * p], fmaf(v[2 * p + 1], v[2 * p + 1], s[2 * p + 1]));
-                }
-              }
-            }
-          } else {  // fp32 NCHW, first out_c channels (final conv -> eps)
-            if (valid && cb == 0) {
-              float* o = reinterpret_cast<float*>(L.out);
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (c < L.out_c) o[((size_t(b) * L.out_c + c) * L.H + y) * L.W + x] = v[c];
+              for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + (cb + 1) * 4 + k, valid);
             }
           }
-        }
-        if (do_stats) {
-          // fixed-order reduction: registers (mt) -> lanes (butterfly) -> this warp's slot row
-          const float tot = warp_transpose_reduce32(s, lane);
-          tstat[q * 256 + cb * 32 + lane] = tot;
+          if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.out) + pix * N + cb * 32);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint4 u;
+              u.x = Cvt<T>::pack(v[k * 8 + 0], v[k * 8 + 1]);
+              u.y = Cvt<T>::pack(v[k * 8 + 2], v[k * 8 + 3]);
+              u.z = Cvt<T>::pack(v[k * 8 + 4], v[k * 8 + 5]);
+              u.w = Cvt<T>::pack(v[k * 8 + 6], v[k * 8 + 7]);
+              op[k] = u;
+            }
+          }
+          if (do_stats) {
+            // in place: v[2p] <- pair sum, v[2p+1] <- pair sum of squares (zero for masked rows)
+            if (all_valid) {
+#pragma unroll
+              for (int p = 0; p < 16; ++p) {
+                const float a = v[2 * p], c2 = v[2 * p + 1];
+                v[2 * p] = a + c2;
+                v[2 * p + 1] = fmaf(a, a, c2 * c2);
+              }
+            } else {
+#pragma unroll
+              for (int p = 0; p < 16; ++p) {
+                const float a = valid ? v[2 * p] : 0.f, c2 = valid ? v[2 * p + 1] : 0.f;
+                v[2 * p] = a + c2;
+                v[2 * p + 1] = fmaf(a, a, c2 * c2);
+              }
+            }
+            if (Cfg::kStatsInTmem) {
+              // per-lane running sums in spare TMEM columns; lanes are reduced when the sample changes
+              uint32_t run[32];
+              tmem_ld32(run_addr + cb * 32, run);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) run[j] = __float_as_uint(__uint_as_float(run[j]) + v[j]);
+              tmem_st32(run_addr + cb * 32, run);
+            } else {
+              const float tot = warp_transpose_reduce32(v, lane);
+              tstat[ew * kRow + cb * 32 + lane] = tot;
+            }
+          }
+        } else {  // fp32 NCHW, first out_c channels (final conv -> eps)
+          if (valid && cb == 0) {
+            float* o = reinterpret_cast<float*>(L.out);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < L.out_c) o[((size_t(b) * L.out_c + c) * H + y) * W + x] = v[c];
+          }
         }
       }
+      if (Cfg::kStatsInTmem && do_stats) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+      PROF_MARK(1);
       if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
-      if (do_stats) {
-        // warps in fixed order, then order-independent 64-bit fixed-point atomics: the statistics
-        // (and therefore every activation) are bitwise reproducible run to run
-        named_bar_sync(2, 128);
-        for (int i = et; i < N; i += 128) {
-          const float tsum = ((tstat[i] + tstat[256 + i]) + tstat[512 + i]) + tstat[768 + i];
-          atomicAdd(L.out_stats + size_t(b) * N + i,
-                    static_cast<unsigned long long>(__double2ll_rn(double(tsum) * kStatScale)));
-        }
-        named_bar_sync(2, 128);
+      // next tile coordinates (no divisions in the loop)
+      const int b_cur = b;
+      if (++tx == tiles_x) {
+        tx = 0;
+        if (++ty == L.tiles_y) { ty = 0; ++b; }
       }
+      if (do_stats) {
+        const bool flush = !Cfg::kStatsInTmem || (tile + 1) % tgroup == 0;
+        if (flush) {
+          if (Cfg::kStatsInTmem) {
+            for (int cb = 0; cb < Cfg::kNcb; ++cb) {
+              uint32_t run[32];
+              float fv[32];
+              tmem_ld32(run_addr + cb * 32, run);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                fv[j] = __uint_as_float(run[j]);
+                run[j] = 0u;
+              }
+              tmem_st32(run_addr + cb * 32, run);
+              const float tot = warp_transpose_reduce32(fv, lane);
+              tstat[ew * kRow + cb * 32 + lane] = tot;
+            }
+            tmem_st_wait();
+          }
+          // warps in fixed order, then order-independent 64-bit fixed-point atomics: the statistics
+          // (and therefore every activation) are bitwise reproducible run to run
+          named_bar_sync(2, kEpiThreads);
+          for (int i = et; i < N; i += kEpiThreads) {
+            float tsum = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += tstat[w8 * kRow + i];
+            atomicAdd(L.out_stats + size_t(b_cur) * N + i,
+                      static_cast<unsigned long long>(__float2ll_rn(tsum * float(kStatScale))));
+          }
+          named_bar_sync(2, kEpiThreads);
+        }
+      }
+      PROF_MARK(2);
     }
+    if (et == 0) PROF_FLUSH(1);
   } else {
     // =========================================================== input producers
-    const int pw = warp < 4 ? warp - 2 : warp - 6;  // 0..9
-    const int pidx = pw * 32 + lane;                 // 0..319
+    const int pw = warp < 4 ? warp - 2 : warp - 10;  // warps 2,3,12..19 -> 0..9
+    const int pidx = pw * 32 + lane;                  // 0..319
     const int lg = ncg == 8 ? 3 : (ncg == 4 ? 2 : (ncg == 2 ? 1 : 0));
     const int cg = pidx & (ncg - 1);
     const int nunits = kPatchPos * ncg;
+    const int H = L.H, W = L.W, mode = L.mode, tiles_x = L.tiles_x;
+    // per-thread patch coordinates of the (up to) 9 16-byte units it fills: fixed for the launch
+    uint32_t pcoord[kMaxUnits];  // py | px << 8 | exists << 16
+#pragma unroll
+    for (int i = 0; i < kMaxUnits; ++i) {
+      const int u = pidx + i * kProdThreads;
+      const int pos = u >> lg;
+      const int py = pos / kPatchW, px = pos - py * kPatchW;
+      bool ex = u < nunits;
+      if (mode == kModeS2D && (py > kTileH || px > kTileW)) ex = false;  // 33x9 block patch
+      pcoord[i] = uint32_t(py) | (uint32_t(px) << 8) | (ex ? 0x10000u : 0u);
+    }
+    const int shl = mode == kModeS2D ? 1 : 0, shr = mode == kModeUp2x ? 1 : 0;
+    const int src_w = mode == kModeS2D ? 2 * W : (mode == kModeUp2x ? (W >> 1) : W);
+    __half* table_h = reinterpret_cast<__half*>(table);
     int as = 0, aph = 0, cur_b = -1;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_img;
-      const int rem = tile - b * tiles_per_img;
-      const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
+    int b = tile_begin / tiles_per_img;
+    int rem = tile_begin - b * tiles_per_img;
+    int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    PROF_DECL;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
 
       // ---- GroupNorm scale/shift table for this sample
@@ -347,20 +535,18 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
         const int cpg = L.gn_C / L.gn_groups;
         if (pidx < L.gn_groups) {
           const int ppg = cpg >> 1, p0 = L.src[0].C >> 1;
-          double S = 0.0, Q = 0.0;
+          long long Si = 0, Qi = 0;
           for (int pv = pidx * ppg; pv < (pidx + 1) * ppg; ++pv) {
             const int si = pv < p0 ? 0 : 1;
             const int pl = pv < p0 ? pv : pv - p0;
             const long long* st = reinterpret_cast<const long long*>(L.src[si].stats) +
                                   (size_t(b) * (L.src[si].C >> 1) + pl) * 2;
-            S += double(st[0]);
-            Q += double(st[1]);
+            Si += st[0];
+            Qi += st[1];
           }
-          S *= (1.0 / kStatScale);
-          Q *= (1.0 / kStatScale);
           const double n = double(cpg) * L.src[0].H * L.src[0].W;
-          const double mean = S / n;
-          double var = Q / n - mean * mean;
+          const double mean = double(Si) * (1.0 / kStatScale) / n;
+          double var = double(Qi) * (1.0 / kStatScale) / n - mean * mean;
           var = var > 0.0 ? var : 0.0;
           gstat[pidx] = make_float2(float(mean), float(1.0 / sqrt(var + double(L.gn_eps))));
         }
@@ -368,69 +554,83 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
         for (int c = pidx; c < L.gn_C; c += kProdThreads) {
           const float2 gs = gstat[c / cpg];
           const float sc = L.gamma[c] * gs.y;
-          table[c] = make_float2(sc, L.beta[c] - gs.x * sc);
+          const float sh = L.beta[c] - gs.x * sc;
+          if (kFast) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
+            table_h[c] = __float2half_rn(0.5f * sc);
+            table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
+          } else {
+            table[c] = make_float2(sc, sh);
+          }
         }
         named_bar_sync(1, kProdThreads);
       }
 
-      // ---- per-thread source pixel offsets of the patch positions it fills (-1 = zero padding)
+      // ---- source pixel offsets of this thread's patch positions (-1 = zero padding)
       int pixoff[kMaxUnits];
 #pragma unroll
       for (int i = 0; i < kMaxUnits; ++i) {
-        const int u = pidx + i * kProdThreads;
-        const int pos = u >> lg;
-        const int py = pos / kPatchW, px = pos - py * kPatchW;
-        const int y = y0 + py, x = x0 + px;
-        int off = -1;
-        if (u < nunits && y >= 0 && y < L.H && x >= 0 && x < L.W) {
-          if (L.mode == kModeNormal) off = y * L.W + x;
-          else if (L.mode == kModeUp2x) off = (y >> 1) * (L.W >> 1) + (x >> 1);
-          else if (py <= kTileH && px <= kTileW) off = (2 * y) * (2 * L.W) + 2 * x;
-        }
-        pixoff[i] = off;
+        const int y = y0 + int(pcoord[i] & 0xffu), x = x0 + int((pcoord[i] >> 8) & 0xffu);
+        const bool ok =
+            (pcoord[i] >> 16) != 0u && unsigned(y) < unsigned(H) && unsigned(x) < unsigned(W);
+        const int off = ((y << shl) >> shr) * src_w + ((x << shl) >> shr);
+        pixoff[i] = ok ? off : -1;
       }
+      PROF_MARK(0);
 
       for (int c = 0; c < L.nchunks; ++c) {
         const ConvChunk& ck = L.chunk[c];
         const ConvSrc& s = L.src[ck.src];
         const int sC = s.C;
+        const bool gn = ck.gn != 0;
         const T* base = reinterpret_cast<const T*>(s.ptr) +
                         (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8;
         uint4 rv[kMaxUnits];
 #pragma unroll
-        for (int i = 0; i < kMaxUnits; ++i) {
-          rv[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (pixoff[i] >= 0) rv[i] = *reinterpret_cast<const uint4*>(base + size_t(pixoff[i]) * sC);
-        }
+        for (int i = 0; i < kMaxUnits; ++i)
+          rv[i] = ldg16_pred(base + size_t(pixoff[i] < 0 ? 0 : pixoff[i]) * sC, pixoff[i] >= 0);
         float sc[8], sh[8];
-        if (ck.gn) {
+        uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
+        if (gn) {
+          if (kFast) {
+            hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cg * 8);
+            hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cg * 8);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 e = table[ck.vc0 + cg * 8 + j];
-            sc[j] = e.x;
-            sh[j] = e.y;
+            for (int j = 0; j < 8; ++j) {
+              const float2 e = table[ck.vc0 + cg * 8 + j];
+              sc[j] = e.x;
+              sh[j] = e.y;
+            }
           }
         }
+        PROF_MARK(1);
         mbar_wait(bar_a_empty(as), aph ^ 1);
-        const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes;
+        PROF_MARK(2);
+        const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes + uint32_t(pidx >> lg) * 16;
 #pragma unroll
         for (int i = 0; i < kMaxUnits; ++i) {
-          const int u = pidx + i * kProdThreads;
-          if (u < nunits) {
+          if (pidx + i * kProdThreads < nunits) {
             uint4 o = rv[i];
-            if (ck.gn && pixoff[i] >= 0) {
-              const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
-              uint32_t r4[4];
+            if (gn && pixoff[i] >= 0) {
+              if (kFast) {
+                o.x = swish_h2(o.x, hsc.x, hsh.x);
+                o.y = swish_h2(o.y, hsc.y, hsh.y);
+                o.z = swish_h2(o.z, hsc.z, hsh.z);
+                o.w = swish_h2(o.w, hsc.w, hsh.w);
+              } else {
+                const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+                uint32_t r4[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = Cvt<T>::unpack(w4[e]);
-                const float a = swish_f(fmaf(f.x, sc[2 * e], sh[2 * e]));
-                const float bb = swish_f(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
-                r4[e] = Cvt<T>::pack(a, bb);
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = Cvt<T>::unpack(w4[e]);
+                  const float a = swish_f(fmaf(f.x, sc[2 * e], sh[2 * e]));
+                  const float bb = swish_f(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
+                  r4[e] = Cvt<T>::pack(a, bb);
+                }
+                o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
               }
-              o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
             }
-            const uint32_t dst = dst0 + uint32_t(u >> lg) * 16;
+            const uint32_t dst = dst0 + uint32_t((i * kProdThreads) >> lg) * 16;
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y),
                          "r"(o.z), "r"(o.w)
                          : "memory");
@@ -439,9 +639,15 @@ conv_gemm_kernel(const ConvLayer* __restrict__ layer_g, int t_step) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a_full(as));
+        PROF_MARK(3);
         if (++as == kAStages) { as = 0; aph ^= 1; }
       }
+      if (++tx == tiles_x) {
+        tx = 0;
+        if (++ty == L.tiles_y) { ty = 0; ++b; }
+      }
     }
+    if (pidx == 0) PROF_FLUSH(2);
   }
 
   tc_fence_before();

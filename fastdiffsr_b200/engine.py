@@ -182,6 +182,15 @@ class Engine:
         return [(self.lib.fdsr_debug_op_name(self._h, i).decode(), float(ms[i]),
                  float(self.lib.fdsr_debug_op_flops(self._h, i))) for i in range(n)]
 
+    def role_cycles(self, op: int, t: int = 0):
+        """(n_cta, 4 roles, 8 slots) cycle counters of conv op `op` (FDSR_PROFILE builds only)."""
+        n = 148 * 32 * 2
+        buf = (C.c_int64 * n)()
+        with torch.cuda.device(self.device):
+            m = self._check(self.lib.fdsr_debug_role_cycles(self._h, op, t, buf, n, self._stream()),
+                            "fdsr_debug_role_cycles")
+        return np.array(buf[:m], dtype=np.int64).reshape(-1, 4, 8)
+
     def launch_count(self):
         return int(self.lib.fdsr_launch_count(self._h))
 

@@ -139,6 +139,10 @@ const char* fdsr_debug_op_name(const fdsr_ctx* ctx, int32_t i);
 double fdsr_debug_op_flops(const fdsr_ctx* ctx, int32_t i);
 int fdsr_debug_profile_unet(fdsr_ctx* ctx, int32_t t, int32_t reps, float* ms_out_host, int32_t cap,
                             void* stream);
+/* Role-level cycle counters of one conv op (only populated by -DFDSR_PROFILE builds of the library,
+ * used by tools/role_profile.py): out_host[(cta*4 + role)*8 + slot], role 0 = MMA issuer, 1 = epilogue,
+ * 2 = producer.  Re-runs op `op` on the current buffers; returns the number of entries.  Synchronous. */
+int fdsr_debug_role_cycles(fdsr_ctx* ctx, int32_t op, int32_t t, int64_t* out_host, int32_t cap, void* stream);
 /* Kernel launches enqueued by this context so far (library kernels only). */
 int64_t fdsr_launch_count(const fdsr_ctx* ctx);
 /* Algorithmic conv FLOPs (2*MAC, padding counted) of one UNet forward at the reserved shape. */
