@@ -26,6 +26,7 @@ struct HTensor {
   std::string name;
   int C = 0, level = 0;
   bool stats = false;
+  int unit = 0;  // gcd (channels) of the GroupNorm units every consumer needs; 0 = no GroupNorm consumer
   size_t off = 0, stats_off = 0;  // byte offsets inside the workspace
 };
 
@@ -114,6 +115,7 @@ struct fdsr_ctx {
   // graph cache
   bool use_graph = true;
   bool precise = false;  // FDSR_PRECISE_SWISH=1: fp32 Swish in the producers
+  bool tma_store = true; // FDSR_TMA_STORE=0: per-lane 16-byte stores in the epilogue
   cudaGraphExec_t graph = nullptr;
   struct {
     int B = 0, H = 0, W = 0;
@@ -351,6 +353,20 @@ int build_plan(fdsr_ctx* c) {
     c->ops.push_back({0, int(c->convs.size()) - 1});
   }
   c->t_last = cur;
+  // Statistics granularity per tensor: a consumer GroupNorm with cpg channels per group over the
+  // virtual concat [src0 (C0), src1] can use entries of gcd(cpg, C0) channels (cpg when un-concatenated).
+  auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+  for (const HConv& k : c->convs) {
+    if (k.gn_C == 0) continue;
+    const int cpg = k.gn_C / g.norm_groups;
+    const int unit = k.gn_nsrc == 2 ? gcd(cpg, c->tensors[k.src[0]].C) : cpg;
+    for (int s = 0; s < k.gn_nsrc; ++s) {
+      HTensor& t = c->tensors[k.src[s]];
+      t.unit = t.unit ? gcd(t.unit, unit) : unit;
+    }
+  }
+  for (HTensor& t : c->tensors)
+    if (t.stats && t.unit == 0) t.stats = false;  // nobody normalises this tensor
   // sanity + algorithmic FLOPs (2*MAC, padding counted, real channels only)
   double fl = 0.0;
   for (const HConv& k : c->convs) {
@@ -521,6 +537,35 @@ int build_bias_tables(fdsr_ctx* c) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC 16-bit activation [B][H][W][C] as a rank-4 TMA tensor {C, W, H, B}, box {32, 8, 4, 1}, 64B swizzle
+bool make_out_map(CUtensorMap* m, void* ptr, int B, int H, int W, int C, bool bf16) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+  const cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+  const cuuint32_t box[4] = {32, cuuint32_t(kTileW), 4, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int upload_layers(fdsr_ctx* c) {
   const int B = c->B, H = c->H, W = c->W;
   if (!c->d_prof) {
@@ -579,7 +624,13 @@ int upload_layers(fdsr_ctx* c) {
     if (k.out_mode == kOutAct) {
       const HTensor& t = c->tensors[k.out];
       l.out = c->d_ws + t.off;
+      l.use_tma_store = (c->tma_store && k.N >= 32 &&
+                         make_out_map(&l.out_map, l.out, B, l.H, l.W, k.N, c->cfg.dtype == FDSR_DTYPE_BF16))
+                            ? 1 : 0;
       l.out_stats = t.stats ? reinterpret_cast<unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
+      int su = 1;
+      while (su < 8 && t.unit % (4 * su) == 0) su *= 2;  // largest power of two with 2*su | unit, <= 8 pairs
+      l.out_su = (k.N == 64) ? 1 : su;                    // N = 64 keeps per-pair running sums in TMEM
     } else {
       l.out = c->d_ws + c->off_eps;
     }
@@ -593,6 +644,10 @@ int upload_layers(fdsr_ctx* c) {
       l.group = (k.N == 64 && tpi % 2 == 0) ? 2 : 1;
     }
     l.prof = c->d_prof;
+    {
+      const char* e = getenv("FDSR_DBG_SKIP");
+      l.dbg = e ? atoi(e) : 0;
+    }
   }
   static_assert(sizeof(ConvLayer) <= 4000, "ConvLayer must fit the kernel parameter space");
   c->h_layers = L;
@@ -831,6 +886,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
   {
     const char* e = getenv("FDSR_PRECISE_SWISH");
     c->precise = e && e[0] == '1';
+    const char* e2 = getenv("FDSR_TMA_STORE");
+    c->tma_store = !(e2 && e2[0] == '0');
   }
   if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
     delete c;

@@ -7,6 +7,7 @@
 // list of taps (a shifted view of the resident input patch x a packed weight blob).
 #pragma once
 #include <cstdint>
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace fdsr {
 
@@ -54,6 +55,9 @@ struct ConvSrc {
 };
 
 struct ConvLayer {
+  // TMA descriptor of the 16-bit NHWC output tensor, dims {C, W, H, B}, box {32 ch, 8, 4, 1},
+  // 64B swizzle: each epilogue warp stores its 32 px x 32 ch block with one bulk tensor copy
+  alignas(64) CUtensorMap out_map;
   ConvSrc src[kMaxSrc];
   ConvChunk chunk[kMaxChunks];
   int32_t nchunks;
@@ -75,11 +79,14 @@ struct ConvLayer {
   const void* resid;    // identity residual, NHWC 16-bit with N channels, or null
   void* out;            // NHWC 16-bit [B][H][W][N]  |  fp32 NCHW [B][out_c][H][W]
   unsigned long long* out_stats;  // [B][N/2][2] fixed point, or null
+  int32_t use_tma_store;  // 1: out_map is valid
+  int32_t out_su;       // channel pairs per statistics entry (1, 2, 4, 8): coarsest unit every consumer can use
   int32_t out_mode;     // OutMode
   int32_t out_c;
   const uint8_t* weights;  // packed blobs
   int32_t tiles_x, tiles_y, ntiles;
   int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)
+  int32_t dbg;             // experiments (tools/): bit0 skip epilogue work, bit1 skip producer work
   long long* prof;         // role cycle counters [grid][4 roles][8 slots] (FDSR_PROFILE builds only)
 };
 

@@ -38,7 +38,6 @@ constexpr int kProdThreads = kProdWarps * 32;  // 320
 constexpr int kMaxUnits = 9;                   // ceil(340*8 / 320)
 constexpr int kEpiWarps = 8;                   // warps 4..11: (warp % 4) = TMEM lane quarter, (warp-4)/4 = MMA tile
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kAStages = 2;
 constexpr int kMaxGnC = 512;
 // GroupNorm statistics are accumulated as 64-bit fixed point (2^-24 resolution): integer atomics
 // are associative, so the sums do not depend on the order in which CTAs finish.
@@ -57,7 +56,10 @@ struct ConvCfg {
       kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
   // a B stage holds as many consecutive tap blobs of one chunk as fit (N=64: 4 taps, 128: 2, 256: 1)
   static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : 32768;
-  static constexpr int kBStages = N >= 256 ? 3 : (N < 32 ? 2 : 4);
+  // N <= 128 layers are bounded by the producer/epilogue roles, not by weight streaming: give the
+  // input patch a third stage (deeper decoupling of producers and MMA) and the weights two.
+  static constexpr int kAStages = N >= 256 ? 2 : 3;
+  static constexpr int kBStages = N >= 256 ? 3 : 2;
   static constexpr int kNcb = N < 32 ? 1 : N / 32;
   static constexpr int kRow = N < 32 ? 32 : N;  // floats per epilogue-warp statistics row
   // shared memory carve-up (bytes)
@@ -70,7 +72,9 @@ struct ConvCfg {
   static constexpr int kOffBar = kOffTstat + kEpiWarps * kRow * 4;  // one row of pair sums per epilogue warp
   static constexpr int kNumBar = 2 * kAStages + 2 * kBStages + 2 * kNumAcc;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
-  static constexpr int kSmemBytes = kOffTmem + 16;
+  // per-epilogue-warp 2 KB staging block for the TMA store of 32 px x 32 ch (64B-swizzled)
+  static constexpr int kOffStage = ((kOffTmem + 16 + 1023) / 1024) * 1024;
+  static constexpr int kSmemBytes = kOffStage + (N < 32 ? 0 : kEpiWarps * 2048);
 };
 
 template <typename T>
@@ -137,18 +141,29 @@ __device__ __forceinline__ uint4 ldg16_pred(const void* p, bool pred) {
   return v;
 }
 
-// Sum v[j] over the 32 lanes of a warp for all 32 j at once; lane l returns the total of v[l].
-__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+// Transposing warp reduction: sum v[j] over the 32 lanes for all j at once.
+// Generalisation to NV = 32, 16, 8 or 4 values per lane: lane l returns the 32-lane total of
+// v[l >> (5 - log2 NV)] (replicated over 32/NV consecutive lanes).
+template <int NV, int OFF, int NH>
+struct TransposeReduceStep {
+  __device__ static __forceinline__ void run(float (&v)[NV], int lane) {
+    if constexpr (NH >= 1) {
+      const bool up = (lane & OFF) != 0;
 #pragma unroll
-  for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int j = 0; j < n; ++j) {
-      const float keep = up ? v[j + n] : v[j];
-      const float send = up ? v[j] : v[j + n];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      for (int j = 0; j < NH; ++j) {
+        const float keep = up ? v[j + NH] : v[j];
+        const float send = up ? v[j] : v[j + NH];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
     }
+    if constexpr (OFF > 1) TransposeReduceStep<NV, OFF / 2, NH / 2>::run(v, lane);
   }
+};
+template <int NV>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane) {
+  TransposeReduceStep<NV, 16, NV / 2>::run(v, lane);
   return v[0];
 }
 
@@ -178,7 +193,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   using Cfg = ConvCfg<N>;
   constexpr int kRow = Cfg::kRow;
-  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int kAStages = Cfg::kAStages;
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   float2* table = reinterpret_cast<float2*>(smem + Cfg::kOffTable);
@@ -332,11 +348,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const int et = tid - 128;          // 0..255
     const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride;
     for (int i = et; i < kRow; i += kEpiThreads) bias_s[i] = i < N ? bias_g[i] : 0.f;
+    for (int i = et; i < kEpiWarps * kRow; i += kEpiThreads) tstat[i] = 0.f;
     named_bar_sync(2, kEpiThreads);
+    const int su = L.out_su;  // channel pairs per statistics entry (1, 2, 4 or 8)
     const int m = q * 32 + lane, g = m >> 3, r = m & 7;
     const bool act = L.out_mode == kOutAct;
     const bool do_stats = (L.out_stats != nullptr) && act;
     const bool has_res = (L.resid != nullptr) && act;
+    const bool use_tma = (N >= 32) && act && L.use_tma_store != 0;
+    const uint32_t stage_s = smem_u32(smem + Cfg::kOffStage) + uint32_t(ew) * 2048;
     const int H = L.H, W = L.W, tiles_x = L.tiles_x;
     const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
     const uint32_t run_addr = lane_base + Cfg::kStatCol0 + mt * N;  // running sums (kStatsInTmem)
@@ -356,8 +376,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       const int x = tx * kTileW + r, y = ty * kTileH + mt * 16 + g;
       const bool valid = y < H && x < W;
       const bool all_valid = __all_sync(0xffffffffu, valid);
-      const size_t pix = (size_t(b) * H + y) * W + x;
-      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(L.resid) + pix * N);
+      const uint32_t pix = uint32_t((b * H + y) * W + x);  // < 2^31 pixels per tensor
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(L.resid) +
+                                                       size_t(pix) * (N * 2));
+      uint8_t* const orow = reinterpret_cast<uint8_t*>(L.out) + size_t(pix) * (N * 2);
       uint4 rq[4];  // identity residual of the next 32 channels, fetched before it is needed
       if (has_res) {
 #pragma unroll
@@ -368,7 +390,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       tc_fence_after();
       const uint32_t taddr = lane_base + acc * Cfg::kAccCols + mt * Cfg::kAccStride;
 #pragma unroll 1
-      for (int cb = 0; cb < Cfg::kNcb; ++cb) {
+      for (int cb = 0; cb < ((L.dbg & 1) ? 0 : Cfg::kNcb); ++cb) {
         uint32_t raw[32];
         tmem_ld32(taddr + cb * 32, raw);
         tmem_ld_wait();
@@ -399,8 +421,27 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + (cb + 1) * 4 + k, valid);
             }
           }
-          if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.out) + pix * N + cb * 32);
+          if (use_tma && !(L.dbg & 4)) {
+            // stage the warp's 32 px x 32 ch block (64B-swizzled rows), then one bulk tensor store:
+            // full 64-byte segments per pixel instead of 32 scattered 16-byte writes per instruction
+            if (lane == 0) bulk_wait_read0();  // previous store has drained the staging block
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t dst = stage_s + uint32_t(lane) * 64 + uint32_t((k ^ ((lane >> 1) & 3)) * 16);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst),
+                           "r"(Cvt<T>::pack(v[k * 8 + 0], v[k * 8 + 1])), "r"(Cvt<T>::pack(v[k * 8 + 2], v[k * 8 + 3])),
+                           "r"(Cvt<T>::pack(v[k * 8 + 4], v[k * 8 + 5])), "r"(Cvt<T>::pack(v[k * 8 + 6], v[k * 8 + 7]))
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&L.out_map, stage_s, cb * 32, tx * kTileW, ty * kTileH + mt * 16 + q * 4, b);
+              bulk_commit_group();
+            }
+          } else if (valid && !(L.dbg & 4)) {
+            uint4* op = reinterpret_cast<uint4*>(orow + cb * 64);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               uint4 u;
@@ -411,7 +452,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               op[k] = u;
             }
           }
-          if (do_stats) {
+          if (do_stats && !(L.dbg & 8)) {
             // in place: v[2p] <- pair sum, v[2p+1] <- pair sum of squares (zero for masked rows)
             if (all_valid) {
 #pragma unroll
@@ -430,15 +471,59 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             }
             if (Cfg::kStatsInTmem) {
               // per-lane running sums in spare TMEM columns; lanes are reduced when the sample changes
-              uint32_t run[32];
-              tmem_ld32(run_addr + cb * 32, run);
-              tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) run[j] = __float_as_uint(__uint_as_float(run[j]) + v[j]);
-              tmem_st32(run_addr + cb * 32, run);
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t run[16];
+                tmem_ld16(run_addr + cb * 32 + hh * 16, run);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) run[j] = __float_as_uint(__uint_as_float(run[j]) + v[hh * 16 + j]);
+                tmem_st16(run_addr + cb * 32 + hh * 16, run);
+              }
             } else {
-              const float tot = warp_transpose_reduce32(v, lane);
-              tstat[ew * kRow + cb * 32 + lane] = tot;
+              // entry layout per 32 channels: float [pair][2]; a unit of `su` pairs accumulates into
+              // the entry of its first pair (the others stay zero), so consumers need not know `su`
+              float* trow = tstat + ew * kRow + cb * 32;
+              if (su == 1) {
+                const float tot = warp_transpose_reduce<32>(v, lane);
+                trow[lane] = tot;
+              } else if (su == 2) {
+                float w[16];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  w[2 * u] = v[4 * u] + v[4 * u + 2];
+                  w[2 * u + 1] = v[4 * u + 1] + v[4 * u + 3];
+                }
+                const float tot = warp_transpose_reduce<16>(w, lane);
+                const int idx = lane >> 1;
+                if ((lane & 1) == 0) trow[(idx >> 1) * 4 + (idx & 1)] = tot;
+              } else if (su == 4) {
+                float w[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  w[2 * u] = (v[8 * u] + v[8 * u + 2]) + (v[8 * u + 4] + v[8 * u + 6]);
+                  w[2 * u + 1] = (v[8 * u + 1] + v[8 * u + 3]) + (v[8 * u + 5] + v[8 * u + 7]);
+                }
+                const float tot = warp_transpose_reduce<8>(w, lane);
+                const int idx = lane >> 2;
+                if ((lane & 3) == 0) trow[(idx >> 1) * 8 + (idx & 1)] = tot;
+              } else {
+                float w[4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    a0 += v[16 * u + 2 * j];
+                    a1 += v[16 * u + 2 * j + 1];
+                  }
+                  w[2 * u] = a0;
+                  w[2 * u + 1] = a1;
+                }
+                const float tot = warp_transpose_reduce<4>(w, lane);
+                const int idx = lane >> 3;
+                if ((lane & 7) == 0) trow[(idx >> 1) * 16 + (idx & 1)] = tot;
+              }
             }
           }
         } else {  // fp32 NCHW, first out_c channels (final conv -> eps)
@@ -462,7 +547,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         tx = 0;
         if (++ty == L.tiles_y) { ty = 0; ++b; }
       }
-      if (do_stats) {
+      if (do_stats && !(L.dbg & 1)) {
         const bool flush = !Cfg::kStatsInTmem || (tile + 1) % tgroup == 0;
         if (flush) {
           if (Cfg::kStatsInTmem) {
@@ -477,7 +562,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                 run[j] = 0u;
               }
               tmem_st32(run_addr + cb * 32, run);
-              const float tot = warp_transpose_reduce32(fv, lane);
+              const float tot = warp_transpose_reduce<32>(fv, lane);
               tstat[ew * kRow + cb * 32 + lane] = tot;
             }
             tmem_st_wait();
@@ -497,6 +582,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       }
       PROF_MARK(2);
     }
+    if (lane == 0) bulk_wait_all0();  // outstanding bulk tensor stores of this warp
     if (et == 0) PROF_FLUSH(1);
   } else {
     // =========================================================== input producers
@@ -507,15 +593,18 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const int nunits = kPatchPos * ncg;
     const int H = L.H, W = L.W, mode = L.mode, tiles_x = L.tiles_x;
     // per-thread patch coordinates of the (up to) 9 16-byte units it fills: fixed for the launch
-    uint32_t pcoord[kMaxUnits];  // py | px << 8 | exists << 16
+    uint32_t pcoord[kMaxUnits];  // py | px << 8
+    uint32_t emask = 0u, smask = 0u;  // bit i: unit i carries data / unit i has a smem slot to fill
 #pragma unroll
     for (int i = 0; i < kMaxUnits; ++i) {
       const int u = pidx + i * kProdThreads;
       const int pos = u >> lg;
       const int py = pos / kPatchW, px = pos - py * kPatchW;
       bool ex = u < nunits;
+      smask |= ex ? (1u << i) : 0u;
       if (mode == kModeS2D && (py > kTileH || px > kTileW)) ex = false;  // 33x9 block patch
-      pcoord[i] = uint32_t(py) | (uint32_t(px) << 8) | (ex ? 0x10000u : 0u);
+      emask |= ex ? (1u << i) : 0u;
+      pcoord[i] = uint32_t(py) | (uint32_t(px) << 8);
     }
     const int shl = mode == kModeS2D ? 1 : 0, shr = mode == kModeUp2x ? 1 : 0;
     const int src_w = mode == kModeS2D ? 2 * W : (mode == kModeUp2x ? (W >> 1) : W);
@@ -565,29 +654,40 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         named_bar_sync(1, kProdThreads);
       }
 
-      // ---- source pixel offsets of this thread's patch positions (-1 = zero padding)
+      // ---- source pixel offsets of this thread's patch positions; vmask bit i = inside the image
       int pixoff[kMaxUnits];
+      uint32_t vmask = 0u;
 #pragma unroll
       for (int i = 0; i < kMaxUnits; ++i) {
         const int y = y0 + int(pcoord[i] & 0xffu), x = x0 + int((pcoord[i] >> 8) & 0xffu);
-        const bool ok =
-            (pcoord[i] >> 16) != 0u && unsigned(y) < unsigned(H) && unsigned(x) < unsigned(W);
+        const bool ok = ((emask >> i) & 1u) != 0u && unsigned(y) < unsigned(H) && unsigned(x) < unsigned(W);
         const int off = ((y << shl) >> shr) * src_w + ((x << shl) >> shr);
-        pixoff[i] = ok ? off : -1;
+        pixoff[i] = ok ? off : 0;
+        vmask |= ok ? (1u << i) : 0u;
       }
       PROF_MARK(0);
 
       for (int c = 0; c < L.nchunks; ++c) {
+        if (L.dbg & 2) {  // experiment: producers only hand over (stale) stages
+          mbar_wait(bar_a_empty(as), aph ^ 1);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_full(as));
+          if (++as == kAStages) { as = 0; aph ^= 1; }
+          continue;
+        }
         const ConvChunk& ck = L.chunk[c];
         const ConvSrc& s = L.src[ck.src];
         const int sC = s.C;
+        const uint32_t tmask = ck.gn != 0 ? vmask : 0u;  // units that get GroupNorm + Swish
         const bool gn = ck.gn != 0;
-        const T* base = reinterpret_cast<const T*>(s.ptr) +
-                        (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(
+            reinterpret_cast<const T*>(s.ptr) + (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8);
+        const uint32_t pix_bytes = uint32_t(sC) * 2u;
         uint4 rv[kMaxUnits];
 #pragma unroll
         for (int i = 0; i < kMaxUnits; ++i)
-          rv[i] = ldg16_pred(base + size_t(pixoff[i] < 0 ? 0 : pixoff[i]) * sC, pixoff[i] >= 0);
+          rv[i] = ldg16_pred(base + uint32_t(pixoff[i]) * pix_bytes, ((vmask >> i) & 1u) != 0u);
         float sc[8], sh[8];
         uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
         if (gn) {
@@ -609,9 +709,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes + uint32_t(pidx >> lg) * 16;
 #pragma unroll
         for (int i = 0; i < kMaxUnits; ++i) {
-          if (pidx + i * kProdThreads < nunits) {
+          if ((smask >> i) & 1u) {
             uint4 o = rv[i];
-            if (gn && pixoff[i] >= 0) {
+            if ((tmask >> i) & 1u) {
               if (kFast) {
                 o.x = swish_h2(o.x, hsc.x, hsh.x);
                 o.y = swish_h2(o.y, hsc.y, hsh.y);
