@@ -116,6 +116,7 @@ struct fdsr_ctx {
   bool use_graph = true;
   bool precise = false;  // FDSR_PRECISE_SWISH=1: fp32 Swish in the producers
   bool tma_store = true; // FDSR_TMA_STORE=0: per-lane 16-byte stores in the epilogue
+  bool cluster2 = false; // FDSR_CLUSTER=1: 2-CTA clusters with multicast weight stages (measured: no gain yet)
   cudaGraphExec_t graph = nullptr;
   struct {
     int B = 0, H = 0, W = 0;
@@ -676,11 +677,26 @@ cudaError_t set_conv_attrs() {
 template <int N, typename T>
 int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
   const int ngroups = ntiles / c->h_layers[li].group;
-  const int grid = ngroups < c->num_sms ? ngroups : c->num_sms;
+  // clusters of 2 CTAs share (multicast) the weight stages; needs an even number of groups
+  const int cs = (c->cluster2 && ngroups % 2 == 0 && ngroups >= 2) ? 2 : 1;
+  int grid = ngroups < c->num_sms ? ngroups : c->num_sms;
+  grid -= grid % cs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = ConvCfg<N>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (Cvt<T>::kFmt == 0 && !c->precise)
-    conv_gemm_kernel<N, T, Cvt<T>::kFmt == 0><<<grid, kConvThreads, ConvCfg<N>::kSmemBytes, st>>>(c->h_layers[li], t);
+    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, Cvt<T>::kFmt == 0>, c->h_layers[li], t));
   else
-    conv_gemm_kernel<N, T, false><<<grid, kConvThreads, ConvCfg<N>::kSmemBytes, st>>>(c->h_layers[li], t);
+    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false>, c->h_layers[li], t));
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
   return FDSR_OK;
@@ -888,6 +904,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->precise = e && e[0] == '1';
     const char* e2 = getenv("FDSR_TMA_STORE");
     c->tma_store = !(e2 && e2[0] == '0');
+    const char* e3 = getenv("FDSR_CLUSTER");
+    c->cluster2 = e3 && e3[0] == '1';
   }
   if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
     delete c;

@@ -211,6 +211,12 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + Cfg::kNumAcc + s);
   };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
+  // Optional thread-block cluster of 2 CTAs (FDSR_CLUSTER=1): the CTAs walk the same layer in lock
+  // step and share every weight stage — each loads half of it and multicasts it to both, halving
+  // the L2 -> SM weight traffic.  Measured on B200: correct, but no speed-up for this kernel (L2
+  // bandwidth is not its limiter), so it is off by default.
+  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = uint16_t((1u << csize) - 1u);
 
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) {
@@ -219,7 +225,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     }
     for (int s = 0; s < Cfg::kBStages; ++s) {
       mbar_init(bar_b_full(s), 1);
-      mbar_init(bar_b_empty(s), 1);
+      mbar_init(bar_b_empty(s), csize);  // released by the MMA warp of every CTA in the cluster
     }
     for (int s = 0; s < Cfg::kNumAcc; ++s) {
       mbar_init(bar_acc_full(s), 1);
@@ -230,6 +236,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   if (warp == 0) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / copy
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -240,10 +247,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   // the position of the image in the batch (results are bitwise independent of how a batch is sharded).
   const int tgroup = L.group;
   const int ngroups = L.ntiles / tgroup;
-  const int tq = ngroups / int(gridDim.x), tr = ngroups - tq * int(gridDim.x);
-  const int group_begin = int(blockIdx.x) * tq + (int(blockIdx.x) < tr ? int(blockIdx.x) : tr);
-  const int tile_begin = group_begin * tgroup;
-  const int tile_end = (group_begin + tq + (int(blockIdx.x) < tr ? 1 : 0)) * tgroup;
+  // clusters take contiguous runs of `csize` groups ("units"); inside a cluster every CTA gets the
+  // same number of groups, so all CTAs of a cluster consume weight stages at the same cadence
+  const int nclusters = int(gridDim.x / csize), cid = int(blockIdx.x / csize);
+  const int nunits = ngroups / int(csize);
+  const int tq = nunits / nclusters, tr = nunits - tq * nclusters;
+  const int unit_begin = cid * tq + (cid < tr ? cid : tr);
+  const int my_units = tq + (cid < tr ? 1 : 0);
+  const int tile_begin = (unit_begin * int(csize) + int(crank) * my_units) * tgroup;
+  const int tile_end = tile_begin + my_units * tgroup;
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int ncg = L.ncg;
   const uint32_t blob = uint32_t(ncg) * N * 16;  // bytes of one tap's weight blob
@@ -259,8 +271,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // descriptor = hi:lo; hi is constant, lo = (LBO>>4)<<16 | (addr>>4), advanced by plain adds
     const uint32_t a_hi = ((kPatchW * 16) >> 4) | (1u << 14);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo0 = (uint32_t(kPlaneBytes >> 4) << 16) + (sA >> 4);
-    const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16) + (sB >> 4);
+    // (inside a cluster, shared-window addresses carry the CTA rank above bit 18: keep the 18-bit offset)
+    const uint32_t a_lo0 = (uint32_t(kPlaneBytes >> 4) << 16) + ((sA & 0x3FFFFu) >> 4);
+    const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16) + ((sB & 0x3FFFFu) >> 4);
     const int ksteps = ncg >> 1;
     int as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
     PROF_DECL;
@@ -306,7 +319,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                 }
               }
             }
-            umma_commit(bar_b_empty(bs));
+            if (csize > 1) umma_commit_multicast(bar_b_empty(bs), cmask);
+            else umma_commit(bar_b_empty(bs));
             if (tp0 + g >= ntaps) umma_commit(bar_a_empty(as));
             if (tp0 + g >= ntaps && c == L.nchunks - 1) umma_commit(bar_acc_full(acc));
           }
@@ -331,9 +345,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
           mbar_wait(bar_b_empty(bs), bph ^ 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(bar_b_full(bs), uint32_t(g) * blob);
-            bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(tp0) * blob, uint32_t(g) * blob,
-                     bar_b_full(bs));
+            const uint32_t bytes = uint32_t(g) * blob;
+            mbar_arrive_expect_tx(bar_b_full(bs), bytes);  // own slice + the peers' multicast slices
+            if (csize > 1) {
+              const uint32_t slice = bytes / csize;
+              bulk_g2s_multicast(sB + bs * Cfg::kBStageBytes + crank * slice, w + size_t(tp0) * blob + crank * slice,
+                                 slice, bar_b_full(bs), cmask);
+            } else {
+              bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(tp0) * blob, bytes, bar_b_full(bs));
+            }
           }
           __syncwarp();
           if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
@@ -752,6 +772,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it
   if (warp == 0) tmem_dealloc<Cfg::kTmemCols>(tmem);
 }
 
