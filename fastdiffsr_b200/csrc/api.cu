@@ -116,6 +116,8 @@ struct fdsr_ctx {
   bool use_graph = true;
   bool precise = false;  // FDSR_PRECISE_SWISH=1: fp32 Swish in the producers
   bool tma_store = true; // FDSR_TMA_STORE=0: per-lane 16-byte stores in the epilogue
+  bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
+  bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
   bool cluster2 = false; // FDSR_CLUSTER=1: 2-CTA clusters with multicast weight stages (measured: no gain yet)
   cudaGraphExec_t graph = nullptr;
   struct {
@@ -582,7 +584,15 @@ int upload_layers(fdsr_ctx* c) {
     l.B = B;
     l.H = H >> lvl;
     l.W = W >> lvl;
-    l.N = k.N;
+    l.tiles_x = (l.W + kTileW - 1) / kTileW;
+    l.tiles_y = (l.H + kTileH - 1) / kTileH;
+    l.ntiles = B * l.tiles_x * l.tiles_y;
+    // Split-N: a low-resolution layer with fewer 256-pixel tiles than half the SMs is computed as two
+    // 128-column halves by twice as many CTAs.  Only 256 -> 2 x 128: both widths use the same
+    // per-tile statistics path, so results stay bitwise independent of the batch size.
+    l.nsplit = (c->split_n && k.out_mode == kOutAct && k.N == 256 && !c->cluster2 && 2 * l.ntiles <= c->num_sms) ? 2 : 1;
+    l.n_full = k.N;
+    l.N = k.N / l.nsplit;
     l.ncg = k.ncg;
     l.mode = k.mode;
     for (int s = 0; s < k.nsrc; ++s) {
@@ -631,18 +641,15 @@ int upload_layers(fdsr_ctx* c) {
       l.out_stats = t.stats ? reinterpret_cast<unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
       int su = 1;
       while (su < 8 && t.unit % (4 * su) == 0) su *= 2;  // largest power of two with 2*su | unit, <= 8 pairs
-      l.out_su = (k.N == 64) ? 1 : su;                    // N = 64 keeps per-pair running sums in TMEM
+      l.out_su = (l.N == 64) ? 1 : su;                    // N = 64 keeps per-pair running sums in TMEM
     } else {
       l.out = c->d_ws + c->off_eps;
     }
     l.weights = c->d_weights + k.w_off;
-    l.tiles_x = (l.W + kTileW - 1) / kTileW;
-    l.tiles_y = (l.H + kTileH - 1) / kTileH;
-    l.ntiles = B * l.tiles_x * l.tiles_y;
     {
       const int tpi = l.tiles_x * l.tiles_y;
       // running TMEM statistics exist for N = 64 only; the group size must not depend on B
-      l.group = (k.N == 64 && tpi % 2 == 0) ? 2 : 1;
+      l.group = (l.N == 64 && tpi % 2 == 0) ? 2 : 1;
     }
     l.prof = c->d_prof;
     {
@@ -677,22 +684,26 @@ cudaError_t set_conv_attrs() {
 template <int N, typename T>
 int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
   const int ngroups = ntiles / c->h_layers[li].group;
+  const int nsplit = c->h_layers[li].nsplit;
   // clusters of 2 CTAs share (multicast) the weight stages; needs an even number of groups
   const int cs = (c->cluster2 && ngroups % 2 == 0 && ngroups >= 2) ? 2 : 1;
   int grid = ngroups < c->num_sms ? ngroups : c->num_sms;
   grid -= grid % cs;
+  if (nsplit > 1) grid = ngroups * nsplit;  // nsplit CTAs per tile group (chosen so that this fits one wave)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = ConvCfg<N>::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = c->pdl ? 2 : 1;
   if (Cvt<T>::kFmt == 0 && !c->precise)
     CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, Cvt<T>::kFmt == 0>, c->h_layers[li], t));
   else
@@ -708,7 +719,7 @@ int launch_conv(fdsr_ctx* c, int li, int t, cudaStream_t st) {
   const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
   const int h = c->H >> lvl, w = c->W >> lvl;
   const int ntiles = c->B * ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH);
-  switch (k.N) {
+  switch (c->h_layers[li].N) {
     case 16: return launch_conv_t<16, T>(c, li, ntiles, t, st);
     case 64: return launch_conv_t<64, T>(c, li, ntiles, t, st);
     case 128: return launch_conv_t<128, T>(c, li, ntiles, t, st);
@@ -906,6 +917,10 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tma_store = !(e2 && e2[0] == '0');
     const char* e3 = getenv("FDSR_CLUSTER");
     c->cluster2 = e3 && e3[0] == '1';
+    const char* e4 = getenv("FDSR_SPLIT_N");
+    c->split_n = !(e4 && e4[0] == '0');
+    const char* e5 = getenv("FDSR_PDL");
+    c->pdl = !(e5 && e5[0] == '0');
   }
   if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
     delete c;

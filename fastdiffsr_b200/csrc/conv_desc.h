@@ -64,7 +64,9 @@ struct ConvLayer {
   int32_t ncg;          // 16-byte channel groups per chunk (8, or 2 for the 16-channel stem input)
   int32_t mode;         // ConvMode
   int32_t B, H, W;      // output size
-  int32_t N;            // MMA N (padded output channels: 16 / 64 / 128 / 256)
+  int32_t N;            // MMA N of one CTA (16 / 64 / 128 / 256)
+  int32_t n_full;       // channel width of the output tensor and of the packed weight blobs (= N * nsplit)
+  int32_t nsplit;       // CTAs sharing one output tile along N (1 = none): part p owns channels [p*N, p*N+N)
   // GroupNorm over the virtual concat of src[0..nsrc) (only chunks with gn=1 use it)
   int32_t gn_C;         // virtual channels (0 = no GroupNorm in this layer)
   int32_t gn_nsrc;

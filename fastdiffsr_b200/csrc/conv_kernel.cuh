@@ -239,6 +239,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   if (csize > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / copy
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // Programmatic dependent launch: the next layer's CTAs may become resident (and run the prologue
+  // above) as soon as SMs drain; everything that reads or writes activations / statistics waits here
+  // for the previous launch to complete.  The weight loader (warp 1) only touches constant data.
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (warp != 1) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // contiguous, balanced range of tiles for this CTA: consecutive tiles share the sample (GroupNorm
   // table stays valid) and their halos (L2 locality).
@@ -249,7 +254,12 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   const int ngroups = L.ntiles / tgroup;
   // clusters take contiguous runs of `csize` groups ("units"); inside a cluster every CTA gets the
   // same number of groups, so all CTAs of a cluster consume weight stages at the same cadence
-  const int nclusters = int(gridDim.x / csize), cid = int(blockIdx.x / csize);
+  // Split-N (L.nsplit > 1, low-resolution layers whose tile count would leave most SMs idle): CTA
+  // `part` computes output channels [part*N, part*N + N) of the n_full-wide layer for its tiles.
+  const int nsplit = L.nsplit;
+  const int part = int(blockIdx.x) % nsplit;
+  const int n_off = part * N, n_full = L.n_full;
+  const int nclusters = int(gridDim.x / csize) / nsplit, cid = int(blockIdx.x / csize) / nsplit;
   const int nunits = ngroups / int(csize);
   const int tq = nunits / nclusters, tr = nunits - tq * nclusters;
   const int unit_begin = cid * tq + (cid < tr ? cid : tr);
@@ -258,7 +268,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   const int tile_end = tile_begin + my_units * tgroup;
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int ncg = L.ncg;
-  const uint32_t blob = uint32_t(ncg) * N * 16;  // bytes of one tap's weight blob
+  const uint32_t blob = uint32_t(ncg) * N * 16;  // bytes of one tap's weight blob (this CTA's N columns)
+  const uint32_t gblob = uint32_t(ncg) * uint32_t(n_full) * 16;  // the same tap in global memory (all columns)
   const int taps_per_stage =
       int(Cfg::kBStageBytes / blob) < kMaxTaps ? int(Cfg::kBStageBytes / blob) : kMaxTaps;
   const uint32_t sA = smem_u32(smem + Cfg::kOffA);
@@ -339,7 +350,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       for (int c = 0; c < L.nchunks; ++c) {
         const ConvChunk& ck = L.chunk[c];
-        const uint8_t* w = L.weights + ck.w_off;
+        const uint8_t* w = L.weights + size_t(ck.w_off) + size_t(n_off) * 16;
         const int ntaps = ck.ntaps;
         for (int tp0 = 0; tp0 < ntaps; tp0 += taps_per_stage) {
           const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
@@ -351,8 +362,16 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               const uint32_t slice = bytes / csize;
               bulk_g2s_multicast(sB + bs * Cfg::kBStageBytes + crank * slice, w + size_t(tp0) * blob + crank * slice,
                                  slice, bar_b_full(bs), cmask);
-            } else {
+            } else if (nsplit == 1) {
               bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(tp0) * blob, bytes, bar_b_full(bs));
+            } else {
+              // this CTA's N of the n_full columns: one contiguous run per (tap, channel group)
+              uint32_t dst = sB + bs * Cfg::kBStageBytes;
+              for (int tg = 0; tg < g; ++tg) {
+                const uint8_t* wt = w + size_t(tp0 + tg) * gblob;
+                for (int cgi = 0; cgi < ncg; ++cgi, dst += N * 16)
+                  bulk_g2s(dst, wt + size_t(cgi) * n_full * 16, N * 16, bar_b_full(bs));
+              }
             }
           }
           __syncwarp();
@@ -366,7 +385,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const int q = ew & 3;              // TMEM lane quarter owned by this warp (== warp % 4)
     const int mt = ew >> 2;            // which 128-row MMA tile of the CTA tile
     const int et = tid - 128;          // 0..255
-    const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride;
+    const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride + n_off;
     for (int i = et; i < kRow; i += kEpiThreads) bias_s[i] = i < N ? bias_g[i] : 0.f;
     for (int i = et; i < kEpiWarps * kRow; i += kEpiThreads) tstat[i] = 0.f;
     named_bar_sync(2, kEpiThreads);
@@ -398,8 +417,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       const bool all_valid = __all_sync(0xffffffffu, valid);
       const uint32_t pix = uint32_t((b * H + y) * W + x);  // < 2^31 pixels per tensor
       const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(L.resid) +
-                                                       size_t(pix) * (N * 2));
-      uint8_t* const orow = reinterpret_cast<uint8_t*>(L.out) + size_t(pix) * (N * 2);
+                                                       (size_t(pix) * n_full + n_off) * 2);
+      uint8_t* const orow = reinterpret_cast<uint8_t*>(L.out) + (size_t(pix) * n_full + n_off) * 2;
       uint4 rq[4];  // identity residual of the next 32 channels, fetched before it is needed
       if (has_res) {
 #pragma unroll
@@ -457,7 +476,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_4d(&L.out_map, stage_s, cb * 32, tx * kTileW, ty * kTileH + mt * 16 + q * 4, b);
+              tma_store_4d(&L.out_map, stage_s, n_off + cb * 32, tx * kTileW, ty * kTileH + mt * 16 + q * 4, b);
               bulk_commit_group();
             }
           } else if (valid && !(L.dbg & 4)) {
@@ -594,7 +613,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             float tsum = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += tstat[w8 * kRow + i];
-            atomicAdd(L.out_stats + size_t(b_cur) * N + i,
+            atomicAdd(L.out_stats + size_t(b_cur) * n_full + n_off + i,
                       static_cast<unsigned long long>(__float2ll_rn(tsum * float(kStatScale))));
           }
           named_bar_sync(2, kEpiThreads);
@@ -615,6 +634,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // per-thread patch coordinates of the (up to) 9 16-byte units it fills: fixed for the launch
     uint32_t pcoord[kMaxUnits];  // py | px << 8
     uint32_t emask = 0u, smask = 0u;  // bit i: unit i carries data / unit i has a smem slot to fill
+    uint32_t cenmask = 0u;            // bit i: unit i lies in the 32x8 centre of the patch (no halo)
 #pragma unroll
     for (int i = 0; i < kMaxUnits; ++i) {
       const int u = pidx + i * kProdThreads;
@@ -624,6 +644,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       smask |= ex ? (1u << i) : 0u;
       if (mode == kModeS2D && (py > kTileH || px > kTileW)) ex = false;  // 33x9 block patch
       emask |= ex ? (1u << i) : 0u;
+      cenmask |= (py >= 1 && py <= kTileH && px >= 1 && px <= kTileW) ? (1u << i) : 0u;
       pcoord[i] = uint32_t(py) | (uint32_t(px) << 8);
     }
     const int shl = mode == kModeS2D ? 1 : 0, shr = mode == kModeUp2x ? 1 : 0;
@@ -700,6 +721,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         const ConvSrc& s = L.src[ck.src];
         const int sC = s.C;
         const uint32_t tmask = ck.gn != 0 ? vmask : 0u;  // units that get GroupNorm + Swish
+        // a chunk whose only tap is the centre one (1x1 residual conv, one space-to-depth plane) never
+        // reads the halo: neither load nor store it
+        const uint32_t cm = (ck.ntaps == 1 && ck.tap_pos[0] == kPatchW + 1) ? cenmask : 0xffffffffu;
+        const uint32_t lmask = vmask & cm, stmask = smask & cm;
         const bool gn = ck.gn != 0;
         const uint8_t* base = reinterpret_cast<const uint8_t*>(
             reinterpret_cast<const T*>(s.ptr) + (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8);
@@ -707,7 +732,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         uint4 rv[kMaxUnits];
 #pragma unroll
         for (int i = 0; i < kMaxUnits; ++i)
-          rv[i] = ldg16_pred(base + uint32_t(pixoff[i]) * pix_bytes, ((vmask >> i) & 1u) != 0u);
+          rv[i] = ldg16_pred(base + uint32_t(pixoff[i]) * pix_bytes, ((lmask >> i) & 1u) != 0u);
         float sc[8], sh[8];
         uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
         if (gn) {
@@ -729,7 +754,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes + uint32_t(pidx >> lg) * 16;
 #pragma unroll
         for (int i = 0; i < kMaxUnits; ++i) {
-          if ((smask >> i) & 1u) {
+          if ((stmask >> i) & 1u) {
             uint4 o = rv[i];
             if ((tmask >> i) & 1u) {
               if (kFast) {

@@ -36,7 +36,10 @@ struct Params {
   int a_bytes, b_bytes;
   int N;
   int fmt;     // 0 fp16, 1 bf16
-  int layout;  // 0 nosw pitch10 shifted, 1 nosw contiguous (pitch 8, no shift), 2 sw128
+  int layout;  // 0 nosw pitch10 shifted, 1 nosw contiguous (pitch 8, no shift), 2 sw128,
+               // 3 sw128 pixel-major patch (128 B per position, pitch 10, shifted start, SBO = 1280 B) with
+               //   no-swizzle B, 4 = 3 with the patch base 512 B off the 1024-B swizzle period
+  int a_shift; // byte offset of the A image inside shared memory (layout 4)
   int reps;    // MMA repetitions (timing)
   int two_acc; // alternate two accumulators sharing B (timing)
 };
@@ -45,8 +48,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + ((p.a_bytes + 1023) / 1024) * 1024;
+  uint8_t* sA = smem + p.a_shift;
+  uint8_t* sB = smem + ((p.a_shift + p.a_bytes + 1023) / 1024) * 1024;
   const int tid = threadIdx.x, warp = tid >> 5;
 
   for (int i = tid; i < p.a_bytes / 16; i += 128)
@@ -80,10 +83,14 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
         ad[ks] = make_desc_nosw(a0 + (2 * ks) * 128 * 16, 128 * 16, 128);
         ad2[ks] = ad[ks];
         bd[ks] = make_desc_nosw(b0 + (2 * ks) * p.N * 16, p.N * 16, 128);
-      } else {
+      } else if (p.layout == 2) {
         ad[ks] = make_desc_sw128(a0 + ks * 32, 1024);
         ad2[ks] = ad[ks];
         bd[ks] = make_desc_sw128(b0 + ks * 32, 1024);
+      } else {
+        ad[ks] = make_desc_sw128(a0 + BASEPOS * 128 + ks * 32, PITCH * 128);
+        ad2[ks] = make_desc_sw128(a0 + (BASEPOS - 1) * 128 + ks * 32, PITCH * 128);
+        bd[ks] = make_desc_nosw(b0 + (2 * ks) * p.N * 16, p.N * 16, 128);
       }
     }
     const uint32_t tmem2 = (p.two_acc && p.N <= 128) ? tmem + 128 : tmem;
@@ -151,7 +158,7 @@ int main() {
   printf("device %s sm_%d%d SMs %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   int fails = 0;
-  for (int layout = 0; layout < 3; ++layout)
+  for (int layout = 0; layout < 5; ++layout)
     for (int fmt = 0; fmt < 2; ++fmt)
       for (int N : {64, 128, 256}) {
         // logical operands
@@ -159,7 +166,7 @@ int main() {
         srand(1234 + N + fmt);
         for (auto& x : A) x = h2f(f2h((rand() % 2001 - 1000) / 1000.0f, fmt), fmt);
         for (auto& x : B) x = h2f(f2h((rand() % 2001 - 1000) / 1000.0f, fmt), fmt);
-        int a_bytes, b_bytes = N * 128;
+        int a_bytes, b_bytes = N * 128, a_shift = 0;
         std::vector<uint16_t> aimg, bimg(b_bytes / 2, 0);
         if (layout == 0) {
           a_bytes = 8 * APOS * 16;
@@ -175,14 +182,26 @@ int main() {
           for (int m = 0; m < 128; ++m)
             for (int k = 0; k < KTOT; ++k)
               aimg[((k / 8) * 128 + m) * 8 + (k % 8)] = f2h(A[m * KTOT + k], fmt);
-        } else {
+        } else if (layout == 2) {
           a_bytes = 128 * 128;
           aimg.assign(a_bytes / 2, 0);
           for (int m = 0; m < 128; ++m)
             for (int k = 0; k < KTOT; ++k)
               aimg[m * 64 + (((k / 8) ^ (m & 7)) * 8) + (k % 8)] = f2h(A[m * KTOT + k], fmt);
+        } else {
+          // what a SWIZZLE_128B TMA load of the raw NHWC patch would leave in shared memory: position p
+          // at byte p*128, its 16-byte channel groups XOR-ed with bits [7:9] of the absolute address
+          a_shift = layout == 4 ? 512 : 0;
+          a_bytes = APOS * 128;
+          aimg.assign(a_bytes / 2, f2h(77.0f, fmt));
+          for (int m = 0; m < 128; ++m) {
+            int pos = BASEPOS + (m / 8) * PITCH + (m % 8);
+            int phase = (pos + a_shift / 128) & 7;
+            for (int k = 0; k < KTOT; ++k)
+              aimg[pos * 64 + (((k / 8) ^ phase) * 8) + (k % 8)] = f2h(A[m * KTOT + k], fmt);
+          }
         }
-        if (layout < 2) {
+        if (layout != 2) {
           for (int n = 0; n < N; ++n)
             for (int k = 0; k < KTOT; ++k)
               bimg[((k / 8) * N + n) * 8 + (k % 8)] = f2h(B[(size_t)n * KTOT + k], fmt);
@@ -200,8 +219,8 @@ int main() {
         CK(cudaMalloc(&dc, 8));
         CK(cudaMemcpy(da, aimg.data(), a_bytes, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(db, bimg.data(), b_bytes, cudaMemcpyHostToDevice));
-        Params p{da, db, dd, dc, a_bytes, b_bytes, N, fmt, layout, 1, 0};
-        size_t smem = ((a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
+        Params p{da, db, dd, dc, a_bytes, b_bytes, N, fmt, layout, a_shift, 1, 0};
+        size_t smem = ((a_shift + a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
         probe_kernel<<<1, 128, smem>>>(p);
         CK(cudaDeviceSynchronize());
         std::vector<float> D(128 * N);
