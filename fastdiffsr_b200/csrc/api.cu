@@ -116,6 +116,7 @@ struct fdsr_ctx {
   bool use_graph = true;
   bool precise = false;  // FDSR_PRECISE_SWISH=1: fp32 Swish in the producers
   bool tma_store = true; // FDSR_TMA_STORE=0: per-lane 16-byte stores in the epilogue
+  bool tma_in = true;    // FDSR_TMA_IN=0: producer warps gather every input patch (no TMA loads of the A operand)
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
   bool cluster2 = false; // FDSR_CLUSTER=1: 2-CTA clusters with multicast weight stages (measured: no gain yet)
@@ -569,6 +570,20 @@ bool make_out_map(CUtensorMap* m, void* ptr, int B, int H, int W, int C, bool bf
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// NHWC 16-bit source [B][H][W][C] as a rank-4 TMA tensor {C, W, H, B}, box {64 ch, 10, 34, 1}, 128B swizzle:
+// one load = one 64-channel input patch with halo, pixel-major 128-byte rows, zero-filled outside the image
+bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc || C < 64) return false;
+  const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+  const cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+  const cuuint32_t box[4] = {64, cuuint32_t(kPatchW), cuuint32_t(kPatchH), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
+             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int upload_layers(fdsr_ctx* c) {
   const int B = c->B, H = c->H, W = c->W;
   if (!c->d_prof) {
@@ -603,6 +618,11 @@ int upload_layers(fdsr_ctx* c) {
       l.src[s].H = H >> t.level;
       l.src[s].W = W >> t.level;
     }
+    l.a_tma = (c->tma_in && k.mode == kModeNormal && k.ncg == 8) ? 1 : 0;
+    for (int s = 0; s < k.nsrc && l.a_tma; ++s)
+      if (!make_in_map(&l.in_map[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
+                       c->cfg.dtype == FDSR_DTYPE_BF16))
+        l.a_tma = 0;
     l.nchunks = int(k.chunks.size());
     size_t woff = 0;
     for (int j = 0; j < l.nchunks; ++j) {
@@ -921,6 +941,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->split_n = !(e4 && e4[0] == '0');
     const char* e5 = getenv("FDSR_PDL");
     c->pdl = !(e5 && e5[0] == '0');
+    const char* e6 = getenv("FDSR_TMA_IN");
+    c->tma_in = !(e6 && e6[0] == '0');
   }
   if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
     delete c;

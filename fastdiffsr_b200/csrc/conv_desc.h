@@ -23,7 +23,12 @@ constexpr int kPatchH = kTileH + 2;
 constexpr int kPatchPos = kPatchW * kPatchH;  // 340 positions
 constexpr int kPlanePos = 341;                // odd => conflict-free 16B stores across channel groups
 constexpr int kPlaneBytes = kPlanePos * 16;
-constexpr int kAStageBytes = 8 * kPlaneBytes;  // 8 channel groups of 8 channels
+// TMA-fed layers keep the patch pixel-major instead: 128 bytes (64 channels) per position,
+// 128B-swizzled exactly as a SWIZZLE_128B tensor load of the NHWC source leaves it.
+constexpr int kPatchBytesSw = kPatchPos * 128;  // 43,520
+// one A stage holds either layout; 1024-byte multiple so every stage starts on a swizzle period
+constexpr int kAStageBytes = 43 * 1024;
+static_assert(8 * kPlaneBytes <= kAStageBytes && kPatchBytesSw <= kAStageBytes, "A stage too small");
 
 enum ConvMode : int32_t {
   kModeNormal = 0,  // stride-1 3x3 (or 1x1 via a single centre tap), zero padding 1
@@ -58,11 +63,16 @@ struct ConvLayer {
   // TMA descriptor of the 16-bit NHWC output tensor, dims {C, W, H, B}, box {32 ch, 8, 4, 1},
   // 64B swizzle: each epilogue warp stores its 32 px x 32 ch block with one bulk tensor copy
   alignas(64) CUtensorMap out_map;
+  // TMA descriptors of the 16-bit NHWC source tensors, dims {C, W, H, B}, box {64 ch, 10, 34, 1},
+  // 128B swizzle: one bulk tensor load stages a whole (32+2)x(8+2) x 64-channel input patch,
+  // out-of-image positions zero-filled (valid when a_tma = 1)
+  CUtensorMap in_map[kMaxSrc];
   ConvSrc src[kMaxSrc];
   ConvChunk chunk[kMaxChunks];
   int32_t nchunks;
   int32_t ncg;          // 16-byte channel groups per chunk (8, or 2 for the 16-channel stem input)
   int32_t mode;         // ConvMode
+  int32_t a_tma;        // 1: input patches arrive by TMA (kModeNormal, 64-channel chunks); 0: gathered by the producer warps
   int32_t B, H, W;      // output size
   int32_t N;            // MMA N of one CTA (16 / 64 / 128 / 256)
   int32_t n_full;       // channel width of the output tensor and of the packed weight blobs (= N * nsplit)

@@ -32,7 +32,7 @@
 
 namespace fdsr {
 
-constexpr int kConvThreads = 640;              // 20 warps (register file: 96 regs/thread)
+constexpr int kConvThreads = 640;              // 20 warps = 5 per scheduler (register file: 96 regs/thread)
 constexpr int kProdWarps = 10;
 constexpr int kProdThreads = kProdWarps * 32;  // 320
 constexpr int kMaxUnits = 9;                   // ceil(340*8 / 320)
@@ -70,7 +70,7 @@ struct ConvCfg {
   static constexpr int kOffBias = kOffGstat + 64 * 8;
   static constexpr int kOffTstat = kOffBias + 256 * 4;
   static constexpr int kOffBar = kOffTstat + kEpiWarps * kRow * 4;  // one row of pair sums per epilogue warp
-  static constexpr int kNumBar = 2 * kAStages + 2 * kBStages + 2 * kNumAcc;
+  static constexpr int kNumBar = 3 * kAStages + 2 * kBStages + 2 * kNumAcc;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   // per-epilogue-warp 2 KB staging block for the TMA store of 32 px x 32 ch (64B-swizzled)
   static constexpr int kOffStage = ((kOffTmem + 16 + 1023) / 1024) * 1024;
@@ -111,6 +111,30 @@ __device__ __forceinline__ uint32_t swish_h2(uint32_t x, uint32_t sc, uint32_t s
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
   asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
   return o;
+}
+
+// GroupNorm scale/shift + Swish on 8 packed 16-bit activations.
+// kFast: packed fp16 (hsc/hsh hold scale/2, shift/2); otherwise fp32 EX2/RCP with sc/sh.
+template <typename T, bool kFast>
+__device__ __forceinline__ uint4 gn_swish_unit(uint4 o, const uint4& hsc, const uint4& hsh, const float (&sc)[8],
+                                               const float (&sh)[8]) {
+  if (kFast) {
+    o.x = swish_h2(o.x, hsc.x, hsh.x);
+    o.y = swish_h2(o.y, hsc.y, hsh.y);
+    o.z = swish_h2(o.z, hsc.z, hsh.z);
+    o.w = swish_h2(o.w, hsc.w, hsh.w);
+    return o;
+  }
+  const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+  uint32_t r4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = Cvt<T>::unpack(w4[e]);
+    const float a = swish_f(fmaf(f.x, sc[2 * e], sh[2 * e]));
+    const float bb = swish_f(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
+    r4[e] = Cvt<T>::pack(a, bb);
+  }
+  return make_uint4(r4[0], r4[1], r4[2], r4[3]);
 }
 
 // true in exactly one lane of a fully converged warp (elect.sync keeps the uniform datapath usable)
@@ -210,6 +234,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   auto bar_acc_empty = [&](int s) {
     return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + Cfg::kNumAcc + s);
   };
+  auto bar_raw_full = [&](int s) {  // TMA-fed layers: the raw patch of stage s has landed
+    return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + 2 * Cfg::kNumAcc + s);
+  };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
   // Optional thread-block cluster of 2 CTAs (FDSR_CLUSTER=1): the CTAs walk the same layer in lock
   // step and share every weight stage — each loads half of it and multicasts it to both, halving
@@ -222,6 +249,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(bar_a_full(s), kProdWarps);
       mbar_init(bar_a_empty(s), 1);
+      mbar_init(bar_raw_full(s), 1);
     }
     for (int s = 0; s < Cfg::kBStages; ++s) {
       mbar_init(bar_b_full(s), 1);
@@ -243,7 +271,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   // above) as soon as SMs drain; everything that reads or writes activations / statistics waits here
   // for the previous launch to complete.  The weight loader (warp 1) only touches constant data.
   asm volatile("griddepcontrol.launch_dependents;");
-  if (warp != 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (warp != 1) asm volatile("griddepcontrol.wait;" ::: "memory");  // (warp 1: see the loader role)
 
   // contiguous, balanced range of tiles for this CTA: consecutive tiles share the sample (GroupNorm
   // table stays valid) and their halos (L2 locality).
@@ -280,10 +308,18 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // tcgen05 instructions issued by the elected lane)
     const uint32_t idesc = make_idesc_f16(128, N, Cvt<T>::kFmt);
     // descriptor = hi:lo; hi is constant, lo = (LBO>>4)<<16 | (addr>>4), advanced by plain adds
-    const uint32_t a_hi = ((kPatchW * 16) >> 4) | (1u << 14);
+    // A operand: no-swizzle channel-group planes (SBO = 10 positions x 16 B, LBO = plane) when the
+    // producers gather it, 128B-swizzled pixel-major rows (SBO = 10 positions x 128 B, layout type 2)
+    // when TMA delivers it; the hardware swizzle is a function of the absolute shared-memory address
+    // (tools/probe_umma.cu layouts 3/4), so a tap is still just a shifted start address.
+    const bool sw = L.a_tma != 0;
+    const uint32_t a_hi = sw ? (((kPatchW * 128) >> 4) | (1u << 14) | (2u << 29)) : (((kPatchW * 16) >> 4) | (1u << 14));
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
     // (inside a cluster, shared-window addresses carry the CTA rank above bit 18: keep the 18-bit offset)
-    const uint32_t a_lo0 = (uint32_t(kPlaneBytes >> 4) << 16) + ((sA & 0x3FFFFu) >> 4);
+    const uint32_t a_lo0 = ((sw ? 1u : uint32_t(kPlaneBytes >> 4)) << 16) + ((sA & 0x3FFFFu) >> 4);
+    const uint32_t kstep = sw ? 2u : 2u * kPlanePos;  // 16-byte units between K = 16 slices
+    const int pos_sh = sw ? 3 : 0;                    // patch position -> 16-byte units
+    const uint32_t mt1 = uint32_t(16 * kPatchW) << pos_sh;  // second 128-row MMA tile: 16 image rows down
     const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16) + ((sB & 0x3FFFFu) >> 4);
     const int ksteps = ncg >> 1;
     int as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
@@ -307,24 +343,22 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (elect_one()) {
             uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4);
             for (int tg = 0; tg < g; ++tg, b_lo += blob >> 4) {
-              const uint32_t a_lo = a_stage + ck.tap_pos[tp0 + tg];
+              const uint32_t a_lo = a_stage + (uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh);
               const uint32_t accum0 = (c | tp0 | tg) == 0 ? 0u : 1u;
               if (ksteps == 4) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   const uint64_t bd = (uint64_t(b_hi) << 32) | (b_lo + ks * 2 * N);
-                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos);
-                  const uint64_t ad1 =
-                      (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos + 16 * kPatchW);
+                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep);
+                  const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep + mt1);
                   umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
                   umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
                 }
               } else {
                 for (int ks = 0; ks < ksteps; ++ks) {
                   const uint64_t bd = (uint64_t(b_hi) << 32) | (b_lo + ks * 2 * N);
-                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos);
-                  const uint64_t ad1 =
-                      (uint64_t(a_hi) << 32) | (a_lo + ks * 2 * kPlanePos + 16 * kPatchW);
+                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep);
+                  const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep + mt1);
                   umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
                   umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
                 }
@@ -345,15 +379,56 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     }
     if (lane == 0) PROF_FLUSH(0);
   } else if (warp == 1) {
-    // =========================================================== weight loader
+    // =========================================================== loader: weight stages (bulk copies of
+    // pre-packed tap blobs) and, for TMA-fed layers, the input patches (one tensor load per chunk).
+    // Patch loads are issued opportunistically up to kAStages - 1 chunks ahead whenever their stage has
+    // been released, and unconditionally (blocking) before the loader can block on a weight stage of
+    // the same chunk, so the MMA warp never waits for a patch that was not requested.
+    const bool tma_in = L.a_tma != 0;
+    if (tma_in) asm volatile("griddepcontrol.wait;" ::: "memory");  // patches are the previous layer's output
     int bs = 0, bph = 0;
+    const int total = (tile_end - tile_begin) * L.nchunks;
+    int a_next = 0, a_c = 0, a_as = 0, a_aph = 0;
+    int a_b = tile_begin / tiles_per_img;
+    int a_ty, a_tx;
+    {
+      const int rem = tile_begin - a_b * tiles_per_img;
+      a_ty = rem / L.tiles_x;
+      a_tx = rem - a_ty * L.tiles_x;
+    }
+    auto issue_patch = [&]() {  // stage a_as is free: request the patch of chunk a_next
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_raw_full(a_as), kPatchBytesSw);
+        const ConvChunk& ak = L.chunk[a_c];
+        tma_load_4d(&L.in_map[ak.src], sA + a_as * kAStageBytes, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1,
+                    a_ty * kTileH - 1, a_b);
+      }
+      __syncwarp();
+      ++a_next;
+      if (++a_as == kAStages) { a_as = 0; a_aph ^= 1; }
+      if (++a_c == L.nchunks) {
+        a_c = 0;
+        if (++a_tx == L.tiles_x) {
+          a_tx = 0;
+          if (++a_ty == L.tiles_y) { a_ty = 0; ++a_b; }
+        }
+      }
+    };
+    int k = 0;  // chunk counter of this CTA
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      for (int c = 0; c < L.nchunks; ++c) {
+      for (int c = 0; c < L.nchunks; ++c, ++k) {
         const ConvChunk& ck = L.chunk[c];
         const uint8_t* w = L.weights + size_t(ck.w_off) + size_t(n_off) * 16;
         const int ntaps = ck.ntaps;
+        if (tma_in)
+          while (a_next <= k) {
+            mbar_wait(bar_a_empty(a_as), a_aph ^ 1);
+            issue_patch();
+          }
         for (int tp0 = 0; tp0 < ntaps; tp0 += taps_per_stage) {
           const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
+          if (tma_in)
+            while (a_next < total && a_next < k + kAStages && mbar_test(bar_a_empty(a_as), a_aph ^ 1)) issue_patch();
           mbar_wait(bar_b_empty(bs), bph ^ 1);
           if (elect_one()) {
             const uint32_t bytes = uint32_t(g) * blob;
@@ -627,169 +702,218 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // =========================================================== input producers
     const int pw = warp < 4 ? warp - 2 : warp - 10;  // warps 2,3,12..19 -> 0..9
     const int pidx = pw * 32 + lane;                  // 0..319
-    const int lg = ncg == 8 ? 3 : (ncg == 4 ? 2 : (ncg == 2 ? 1 : 0));
-    const int cg = pidx & (ncg - 1);
-    const int nunits = kPatchPos * ncg;
     const int H = L.H, W = L.W, mode = L.mode, tiles_x = L.tiles_x;
-    // per-thread patch coordinates of the (up to) 9 16-byte units it fills: fixed for the launch
-    uint32_t pcoord[kMaxUnits];  // py | px << 8
-    uint32_t emask = 0u, smask = 0u;  // bit i: unit i carries data / unit i has a smem slot to fill
-    uint32_t cenmask = 0u;            // bit i: unit i lies in the 32x8 centre of the patch (no halo)
-#pragma unroll
-    for (int i = 0; i < kMaxUnits; ++i) {
-      const int u = pidx + i * kProdThreads;
-      const int pos = u >> lg;
-      const int py = pos / kPatchW, px = pos - py * kPatchW;
-      bool ex = u < nunits;
-      smask |= ex ? (1u << i) : 0u;
-      if (mode == kModeS2D && (py > kTileH || px > kTileW)) ex = false;  // 33x9 block patch
-      emask |= ex ? (1u << i) : 0u;
-      cenmask |= (py >= 1 && py <= kTileH && px >= 1 && px <= kTileW) ? (1u << i) : 0u;
-      pcoord[i] = uint32_t(py) | (uint32_t(px) << 8);
-    }
-    const int shl = mode == kModeS2D ? 1 : 0, shr = mode == kModeUp2x ? 1 : 0;
-    const int src_w = mode == kModeS2D ? 2 * W : (mode == kModeUp2x ? (W >> 1) : W);
     __half* table_h = reinterpret_cast<__half*>(table);
     int as = 0, aph = 0, cur_b = -1;
     int b = tile_begin / tiles_per_img;
     int rem = tile_begin - b * tiles_per_img;
     int ty = rem / tiles_x, tx = rem - ty * tiles_x;
     PROF_DECL;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
 
-      // ---- GroupNorm scale/shift table for this sample
-      if (L.gn_C > 0 && b != cur_b) {
-        cur_b = b;
-        named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
-        const int cpg = L.gn_C / L.gn_groups;
-        if (pidx < L.gn_groups) {
-          const int ppg = cpg >> 1, p0 = L.src[0].C >> 1;
-          long long Si = 0, Qi = 0;
-          for (int pv = pidx * ppg; pv < (pidx + 1) * ppg; ++pv) {
-            const int si = pv < p0 ? 0 : 1;
-            const int pl = pv < p0 ? pv : pv - p0;
-            const long long* st = reinterpret_cast<const long long*>(L.src[si].stats) +
-                                  (size_t(b) * (L.src[si].C >> 1) + pl) * 2;
-            Si += st[0];
-            Qi += st[1];
-          }
-          const double n = double(cpg) * L.src[0].H * L.src[0].W;
-          const double mean = double(Si) * (1.0 / kStatScale) / n;
-          double var = double(Qi) * (1.0 / kStatScale) / n - mean * mean;
-          var = var > 0.0 ? var : 0.0;
-          gstat[pidx] = make_float2(float(mean), float(1.0 / sqrt(var + double(L.gn_eps))));
+    // GroupNorm scale/shift table of sample `bb` (virtual concat of the GroupNorm sources)
+    auto build_table = [&](int bb) {
+      named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
+      const int cpg = L.gn_C / L.gn_groups;
+      if (pidx < L.gn_groups) {
+        const int ppg = cpg >> 1, p0 = L.src[0].C >> 1;
+        long long Si = 0, Qi = 0;
+        for (int pv = pidx * ppg; pv < (pidx + 1) * ppg; ++pv) {
+          const int si = pv < p0 ? 0 : 1;
+          const int pl = pv < p0 ? pv : pv - p0;
+          const long long* st = reinterpret_cast<const long long*>(L.src[si].stats) +
+                                (size_t(bb) * (L.src[si].C >> 1) + pl) * 2;
+          Si += st[0];
+          Qi += st[1];
         }
-        named_bar_sync(1, kProdThreads);
-        for (int c = pidx; c < L.gn_C; c += kProdThreads) {
-          const float2 gs = gstat[c / cpg];
-          const float sc = L.gamma[c] * gs.y;
-          const float sh = L.beta[c] - gs.x * sc;
-          if (kFast) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
-            table_h[c] = __float2half_rn(0.5f * sc);
-            table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
-          } else {
-            table[c] = make_float2(sc, sh);
-          }
-        }
-        named_bar_sync(1, kProdThreads);
+        const double n = double(cpg) * L.src[0].H * L.src[0].W;
+        const double mean = double(Si) * (1.0 / kStatScale) / n;
+        double var = double(Qi) * (1.0 / kStatScale) / n - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        gstat[pidx] = make_float2(float(mean), float(1.0 / sqrt(var + double(L.gn_eps))));
       }
+      named_bar_sync(1, kProdThreads);
+      for (int c = pidx; c < L.gn_C; c += kProdThreads) {
+        const float2 gs = gstat[c / cpg];
+        const float sc = L.gamma[c] * gs.y;
+        const float sh = L.beta[c] - gs.x * sc;
+        if (kFast) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
+          table_h[c] = __float2half_rn(0.5f * sc);
+          table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
+        } else {
+          table[c] = make_float2(sc, sh);
+        }
+      }
+      named_bar_sync(1, kProdThreads);
+    };
 
-      // ---- source pixel offsets of this thread's patch positions; vmask bit i = inside the image
-      int pixoff[kMaxUnits];
-      uint32_t vmask = 0u;
+    if (L.a_tma != 0) {
+      // ----------------------------------------------------------------- TMA-fed layers: the loader warp's
+      // tensor loads land the raw 128B-swizzled patch in the stage (out-of-image positions zero);
+      // these warps apply GroupNorm + Swish in place and hand the stage to the MMA warp.  The thread
+      // owns 16-byte slot (pidx & 7) of positions (pidx >> 3) + 40 i: byte pidx*16 + i*5120 of the stage
+      // (conflict-free: a warp covers 512 contiguous bytes).  Stage bases are 1024-byte aligned and 40
+      // positions are 5 swizzle periods, so the slot's logical channel group is the same for every i.
+      const int cgs = (pidx & 7) ^ ((pidx >> 3) & 7);
+      const int pos0 = pidx >> 3;
+      const int py0 = pos0 / kPatchW, px0 = pos0 - py0 * kPatchW;  // position of unit i: (py0 + 4 i, px0)
+      const uint32_t smask = pos0 < kPatchPos - 8 * 40 ? 0x1ffu : 0xffu;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        if (L.gn_C > 0 && b != cur_b) {
+          cur_b = b;
+          build_table(b);
+        }
+        // units inside the image (padding must stay zero: swish(GN(0)) != 0)
+        const int y0 = ty * kTileH - 1 + py0, x0 = tx * kTileW - 1 + px0;
+        uint32_t vmask = 0u;
+        if (unsigned(x0) < unsigned(W)) {
 #pragma unroll
-      for (int i = 0; i < kMaxUnits; ++i) {
-        const int y = y0 + int(pcoord[i] & 0xffu), x = x0 + int((pcoord[i] >> 8) & 0xffu);
-        const bool ok = ((emask >> i) & 1u) != 0u && unsigned(y) < unsigned(H) && unsigned(x) < unsigned(W);
-        const int off = ((y << shl) >> shr) * src_w + ((x << shl) >> shr);
-        pixoff[i] = ok ? off : 0;
-        vmask |= ok ? (1u << i) : 0u;
-      }
-      PROF_MARK(0);
-
-      for (int c = 0; c < L.nchunks; ++c) {
-        if (L.dbg & 2) {  // experiment: producers only hand over (stale) stages
-          mbar_wait(bar_a_empty(as), aph ^ 1);
-          fence_proxy_async_smem();
+          for (int i = 0; i < kMaxUnits; ++i) vmask |= unsigned(y0 + 4 * i) < unsigned(H) ? (1u << i) : 0u;
+          vmask &= smask;
+        }
+        PROF_MARK(0);
+        for (int c = 0; c < L.nchunks; ++c) {
+          const ConvChunk& ck = L.chunk[c];
+          mbar_wait(bar_raw_full(as), aph);
+          PROF_MARK(1);
+          if (ck.gn != 0 && !(L.dbg & 2)) {
+            float sc[8], sh[8];
+            uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
+            if (kFast) {
+              hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cgs * 8);
+              hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cgs * 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 e = table[ck.vc0 + cgs * 8 + j];
+                sc[j] = e.x;
+                sh[j] = e.y;
+              }
+            }
+            const uint32_t a0 = sA + as * kAStageBytes + uint32_t(pidx) * 16;
+            uint4 rv[kMaxUnits];
+#pragma unroll
+            for (int i = 0; i < kMaxUnits; ++i)
+              if ((vmask >> i) & 1u) rv[i] = lds128(a0 + i * (40 * 128));
+#pragma unroll
+            for (int i = 0; i < kMaxUnits; ++i)
+              if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_swish_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
+            fence_proxy_async_smem();
+          }
+          PROF_MARK(3);
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_full(as));
           if (++as == kAStages) { as = 0; aph ^= 1; }
-          continue;
         }
-        const ConvChunk& ck = L.chunk[c];
-        const ConvSrc& s = L.src[ck.src];
-        const int sC = s.C;
-        const uint32_t tmask = ck.gn != 0 ? vmask : 0u;  // units that get GroupNorm + Swish
-        // a chunk whose only tap is the centre one (1x1 residual conv, one space-to-depth plane) never
-        // reads the halo: neither load nor store it
-        const uint32_t cm = (ck.ntaps == 1 && ck.tap_pos[0] == kPatchW + 1) ? cenmask : 0xffffffffu;
-        const uint32_t lmask = vmask & cm, stmask = smask & cm;
-        const bool gn = ck.gn != 0;
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(
-            reinterpret_cast<const T*>(s.ptr) + (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8);
-        const uint32_t pix_bytes = uint32_t(sC) * 2u;
-        uint4 rv[kMaxUnits];
-#pragma unroll
-        for (int i = 0; i < kMaxUnits; ++i)
-          rv[i] = ldg16_pred(base + uint32_t(pixoff[i]) * pix_bytes, ((lmask >> i) & 1u) != 0u);
-        float sc[8], sh[8];
-        uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
-        if (gn) {
-          if (kFast) {
-            hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cg * 8);
-            hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cg * 8);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 e = table[ck.vc0 + cg * 8 + j];
-              sc[j] = e.x;
-              sh[j] = e.y;
-            }
-          }
+        if (++tx == tiles_x) {
+          tx = 0;
+          if (++ty == L.tiles_y) { ty = 0; ++b; }
         }
-        PROF_MARK(1);
-        mbar_wait(bar_a_empty(as), aph ^ 1);
-        PROF_MARK(2);
-        const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes + uint32_t(pidx >> lg) * 16;
+      }
+    } else {
+      // ----------------------------------------------------------------- gathered layers (nearest-upsample,
+      // space-to-depth, the 16-channel stem): predicated 16-byte global loads into registers,
+      // GroupNorm + Swish, 16-byte stores into the no-swizzle [channel group][position][8 ch] patch
+      const int lg = ncg == 8 ? 3 : (ncg == 4 ? 2 : (ncg == 2 ? 1 : 0));
+      const int cg = pidx & (ncg - 1);
+      const int nunits = kPatchPos * ncg;
+      // per-thread patch coordinates of the (up to) 9 16-byte units it fills: fixed for the launch
+      uint32_t pcoord[kMaxUnits];  // py | px << 8
+      uint32_t emask = 0u, smask = 0u;  // bit i: unit i carries data / unit i has a smem slot to fill
+      uint32_t cenmask = 0u;            // bit i: unit i lies in the 32x8 centre of the patch (no halo)
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i) {
+        const int u = pidx + i * kProdThreads;
+        const int pos = u >> lg;
+        const int py = pos / kPatchW, px = pos - py * kPatchW;
+        bool ex = u < nunits;
+        smask |= ex ? (1u << i) : 0u;
+        if (mode == kModeS2D && (py > kTileH || px > kTileW)) ex = false;  // 33x9 block patch
+        emask |= ex ? (1u << i) : 0u;
+        cenmask |= (py >= 1 && py <= kTileH && px >= 1 && px <= kTileW) ? (1u << i) : 0u;
+        pcoord[i] = uint32_t(py) | (uint32_t(px) << 8);
+      }
+      const int shl = mode == kModeS2D ? 1 : 0, shr = mode == kModeUp2x ? 1 : 0;
+      const int src_w = mode == kModeS2D ? 2 * W : (mode == kModeUp2x ? (W >> 1) : W);
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
+        if (L.gn_C > 0 && b != cur_b) {
+          cur_b = b;
+          build_table(b);
+        }
+        // ---- source pixel offsets of this thread's patch positions; vmask bit i = inside the image
+        int pixoff[kMaxUnits];
+        uint32_t vmask = 0u;
 #pragma unroll
         for (int i = 0; i < kMaxUnits; ++i) {
-          if ((stmask >> i) & 1u) {
-            uint4 o = rv[i];
-            if ((tmask >> i) & 1u) {
-              if (kFast) {
-                o.x = swish_h2(o.x, hsc.x, hsh.x);
-                o.y = swish_h2(o.y, hsc.y, hsh.y);
-                o.z = swish_h2(o.z, hsc.z, hsh.z);
-                o.w = swish_h2(o.w, hsc.w, hsh.w);
-              } else {
-                const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
-                uint32_t r4[4];
+          const int y = y0 + int(pcoord[i] & 0xffu), x = x0 + int((pcoord[i] >> 8) & 0xffu);
+          const bool ok = ((emask >> i) & 1u) != 0u && unsigned(y) < unsigned(H) && unsigned(x) < unsigned(W);
+          const int off = ((y << shl) >> shr) * src_w + ((x << shl) >> shr);
+          pixoff[i] = ok ? off : 0;
+          vmask |= ok ? (1u << i) : 0u;
+        }
+        PROF_MARK(0);
+        for (int c = 0; c < L.nchunks; ++c) {
+          if (L.dbg & 2) {  // experiment: producers only hand over (stale) stages
+            mbar_wait(bar_a_empty(as), aph ^ 1);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_full(as));
+            if (++as == kAStages) { as = 0; aph ^= 1; }
+            continue;
+          }
+          const ConvChunk& ck = L.chunk[c];
+          const ConvSrc& s = L.src[ck.src];
+          const int sC = s.C;
+          const uint32_t tmask = ck.gn != 0 ? vmask : 0u;  // units that get GroupNorm + Swish
+          // a chunk whose only tap is the centre one (one space-to-depth plane) never reads the halo:
+          // neither load nor store it
+          const uint32_t cm = (ck.ntaps == 1 && ck.tap_pos[0] == kPatchW + 1) ? cenmask : 0xffffffffu;
+          const uint32_t lmask = vmask & cm, stmask = smask & cm;
+          const bool gn = ck.gn != 0;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(
+              reinterpret_cast<const T*>(s.ptr) + (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8);
+          const uint32_t pix_bytes = uint32_t(sC) * 2u;
+          uint4 rv[kMaxUnits];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = Cvt<T>::unpack(w4[e]);
-                  const float a = swish_f(fmaf(f.x, sc[2 * e], sh[2 * e]));
-                  const float bb = swish_f(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
-                  r4[e] = Cvt<T>::pack(a, bb);
-                }
-                o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+          for (int i = 0; i < kMaxUnits; ++i)
+            rv[i] = ldg16_pred(base + uint32_t(pixoff[i]) * pix_bytes, ((lmask >> i) & 1u) != 0u);
+          float sc[8], sh[8];
+          uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
+          if (gn) {
+            if (kFast) {
+              hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cg * 8);
+              hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cg * 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 e = table[ck.vc0 + cg * 8 + j];
+                sc[j] = e.x;
+                sh[j] = e.y;
               }
             }
-            const uint32_t dst = dst0 + uint32_t((i * kProdThreads) >> lg) * 16;
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(o.x), "r"(o.y),
-                         "r"(o.z), "r"(o.w)
-                         : "memory");
           }
+          PROF_MARK(1);
+          mbar_wait(bar_a_empty(as), aph ^ 1);
+          PROF_MARK(2);
+          const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes + uint32_t(pidx >> lg) * 16;
+#pragma unroll
+          for (int i = 0; i < kMaxUnits; ++i) {
+            if ((stmask >> i) & 1u) {
+              uint4 o = rv[i];
+              if ((tmask >> i) & 1u) o = gn_swish_unit<T, kFast>(o, hsc, hsh, sc, sh);
+              sts128(dst0 + uint32_t((i * kProdThreads) >> lg) * 16, o);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_full(as));
+          PROF_MARK(3);
+          if (++as == kAStages) { as = 0; aph ^= 1; }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a_full(as));
-        PROF_MARK(3);
-        if (++as == kAStages) { as = 0; aph ^= 1; }
-      }
-      if (++tx == tiles_x) {
-        tx = 0;
-        if (++ty == L.tiles_y) { ty = 0; ++b; }
+        if (++tx == tiles_x) {
+          tx = 0;
+          if (++ty == L.tiles_y) { ty = 0; ++b; }
+        }
       }
     }
     if (pidx == 0) PROF_FLUSH(2);
