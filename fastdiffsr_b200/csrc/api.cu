@@ -572,12 +572,12 @@ bool make_out_map(CUtensorMap* m, void* ptr, int B, int H, int W, int C, bool bf
 
 // NHWC 16-bit source [B][H][W][C] as a rank-4 TMA tensor {C, W, H, B}, box {64 ch, 10, 34, 1}, 128B swizzle:
 // one load = one 64-channel input patch with halo, pixel-major 128-byte rows, zero-filled outside the image
-bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16) {
+bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16, bool center) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc || C < 64) return false;
   const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
   const cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
-  const cuuint32_t box[4] = {64, cuuint32_t(kPatchW), cuuint32_t(kPatchH), 1};
+  const cuuint32_t box[4] = {64, cuuint32_t(center ? kTileW : kPatchW), cuuint32_t(center ? kTileH : kPatchH), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -621,7 +621,9 @@ int upload_layers(fdsr_ctx* c) {
     l.a_tma = (c->tma_in && k.mode == kModeNormal && k.ncg == 8) ? 1 : 0;
     for (int s = 0; s < k.nsrc && l.a_tma; ++s)
       if (!make_in_map(&l.in_map[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
-                       c->cfg.dtype == FDSR_DTYPE_BF16))
+                       c->cfg.dtype == FDSR_DTYPE_BF16, false) ||
+          !make_in_map(&l.in_map_c[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
+                       c->cfg.dtype == FDSR_DTYPE_BF16, true))
         l.a_tma = 0;
     l.nchunks = int(k.chunks.size());
     size_t woff = 0;
@@ -636,6 +638,7 @@ int upload_layers(fdsr_ctx* c) {
       d.ntaps = int(ch.taps.size());
       d.w_off = int(woff);
       for (int tp = 0; tp < d.ntaps; ++tp) d.tap_pos[tp] = ch.taps[tp].pos;
+      d.center = (l.a_tma && ch.gn == 0 && d.ntaps == 1 && d.tap_pos[0] == kPatchW + 1) ? 1 : 0;
       woff += ch.taps.size() * size_t(k.ncg) * k.N * 16;
     }
     l.gn_C = k.gn_C;

@@ -26,9 +26,11 @@ constexpr int kPlaneBytes = kPlanePos * 16;
 // TMA-fed layers keep the patch pixel-major instead: 128 bytes (64 channels) per position,
 // 128B-swizzled exactly as a SWIZZLE_128B tensor load of the NHWC source leaves it.
 constexpr int kPatchBytesSw = kPatchPos * 128;  // 43,520
-// one A stage holds either layout; 1024-byte multiple so every stage starts on a swizzle period
-constexpr int kAStageBytes = 43 * 1024;
-static_assert(8 * kPlaneBytes <= kAStageBytes && kPatchBytesSw <= kAStageBytes, "A stage too small");
+// one A stage holds either layout.  341 x 128 B: stage s starts (5 s mod 8) rows into the 1024-byte
+// swizzle period, which the in-place transform accounts for (the MMA unit and TMA both swizzle on
+// absolute shared-memory address bits, so they agree on any 128-byte-aligned base).
+constexpr int kAStageBytes = 8 * kPlaneBytes;  // 43,648
+static_assert(kPatchBytesSw <= kAStageBytes && kAStageBytes % 128 == 0, "A stage too small");
 
 enum ConvMode : int32_t {
   kModeNormal = 0,  // stride-1 3x3 (or 1x1 via a single centre tap), zero padding 1
@@ -48,6 +50,7 @@ struct ConvChunk {
   int32_t vc0;        // channel offset on the virtual (concatenated) GroupNorm axis
   int32_t pix_delta;  // extra source pixel offset (parity plane of the space-to-depth view)
   int32_t ntaps;
+  int32_t center;     // 1: TMA-fed raw chunk whose only tap is the centre one: staged as a dense 32x8 box (no halo)
   int32_t w_off;      // byte offset of this chunk's first tap blob inside the layer's weights
   int32_t tap_pos[kMaxTaps];  // A-operand position offset of each tap (dy*kPatchW + dx)
 };
@@ -67,6 +70,7 @@ struct ConvLayer {
   // 128B swizzle: one bulk tensor load stages a whole (32+2)x(8+2) x 64-channel input patch,
   // out-of-image positions zero-filled (valid when a_tma = 1)
   CUtensorMap in_map[kMaxSrc];
+  CUtensorMap in_map_c[kMaxSrc];  // same tensors, box {64 ch, 8, 32, 1}: centre-only chunks (1x1 residual conv)
   ConvSrc src[kMaxSrc];
   ConvChunk chunk[kMaxChunks];
   int32_t nchunks;

@@ -58,6 +58,8 @@ struct ConvCfg {
   static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : 32768;
   // N <= 128 layers are bounded by the producer/epilogue roles, not by weight streaming: give the
   // input patch a third stage (deeper decoupling of producers and MMA) and the weights two.
+  // (Measured: four patch stages with four one-tap weight stages for N = 64 removes the a_full waits
+  // of the GroupNorm + 1x1-residual layers but starves the MMA warp of weights: 101 -> 132 us.)
   static constexpr int kAStages = N >= 256 ? 2 : 3;
   static constexpr int kBStages = N >= 256 ? 3 : 2;
   static constexpr int kNcb = N < 32 ? 1 : N / 32;
@@ -313,13 +315,14 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // when TMA delivers it; the hardware swizzle is a function of the absolute shared-memory address
     // (tools/probe_umma.cu layouts 3/4), so a tap is still just a shifted start address.
     const bool sw = L.a_tma != 0;
-    const uint32_t a_hi = sw ? (((kPatchW * 128) >> 4) | (1u << 14) | (2u << 29)) : (((kPatchW * 16) >> 4) | (1u << 14));
+    const uint32_t a_hi_full = sw ? (((kPatchW * 128) >> 4) | (1u << 14) | (2u << 29)) : (((kPatchW * 16) >> 4) | (1u << 14));
+    const uint32_t a_hi_cen = ((kTileW * 128) >> 4) | (1u << 14) | (2u << 29);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
     // (inside a cluster, shared-window addresses carry the CTA rank above bit 18: keep the 18-bit offset)
     const uint32_t a_lo0 = ((sw ? 1u : uint32_t(kPlaneBytes >> 4)) << 16) + ((sA & 0x3FFFFu) >> 4);
     const uint32_t kstep = sw ? 2u : 2u * kPlanePos;  // 16-byte units between K = 16 slices
     const int pos_sh = sw ? 3 : 0;                    // patch position -> 16-byte units
-    const uint32_t mt1 = uint32_t(16 * kPatchW) << pos_sh;  // second 128-row MMA tile: 16 image rows down
+    const uint32_t mt1_full = uint32_t(16 * kPatchW) << pos_sh;  // second 128-row MMA tile: 16 image rows down
     const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16) + ((sB & 0x3FFFFu) >> 4);
     const int ksteps = ncg >> 1;
     int as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
@@ -335,6 +338,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         mbar_wait(bar_a_full(as), aph);
         PROF_MARK(1);
         const uint32_t a_stage = a_lo0 + as * (kAStageBytes >> 4);
+        // centre-box chunk (raw single-tap chunk of a TMA-fed layer): dense 32x8 positions, no halo
+        const bool cen = ck.center != 0;
+        const uint32_t a_hi = cen ? a_hi_cen : a_hi_full;
+        const uint32_t mt1 = cen ? uint32_t(16 * kTileW) << 3 : mt1_full;
         for (int tp0 = 0; tp0 < ntaps; tp0 += taps_per_stage) {
           const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
           mbar_wait(bar_b_full(bs), bph);
@@ -343,7 +350,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (elect_one()) {
             uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4);
             for (int tg = 0; tg < g; ++tg, b_lo += blob >> 4) {
-              const uint32_t a_lo = a_stage + (uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh);
+              const uint32_t a_lo = a_stage + (cen ? 0u : uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh);
               const uint32_t accum0 = (c | tp0 | tg) == 0 ? 0u : 1u;
               if (ksteps == 4) {
 #pragma unroll
@@ -381,14 +388,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   } else if (warp == 1) {
     // =========================================================== loader: weight stages (bulk copies of
     // pre-packed tap blobs) and, for TMA-fed layers, the input patches (one tensor load per chunk).
-    // Patch loads are issued opportunistically up to kAStages - 1 chunks ahead whenever their stage has
-    // been released, and unconditionally (blocking) before the loader can block on a weight stage of
-    // the same chunk, so the MMA warp never waits for a patch that was not requested.
+    // Two independent cursors polled in one loop: a patch is requested the moment its stage is
+    // released (up to kAStages chunks ahead of the MMA warp), a weight stage the moment it is free.
+    // GroupNorm chunks land on raw_full (the producer warps transform them in place and then arrive on
+    // a_full); raw chunks complete a_full directly, so the MMA warp starts as soon as the bytes are there.
     const bool tma_in = L.a_tma != 0;
     if (tma_in) asm volatile("griddepcontrol.wait;" ::: "memory");  // patches are the previous layer's output
-    int bs = 0, bph = 0;
     const int total = (tile_end - tile_begin) * L.nchunks;
-    int a_next = 0, a_c = 0, a_as = 0, a_aph = 0;
+    // patch cursor
+    int a_next = tma_in ? 0 : total, a_c = 0, a_as = 0, a_aph = 0;
     int a_b = tile_begin / tiles_per_img;
     int a_ty, a_tx;
     {
@@ -396,54 +404,65 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       a_ty = rem / L.tiles_x;
       a_tx = rem - a_ty * L.tiles_x;
     }
-    auto issue_patch = [&]() {  // stage a_as is free: request the patch of chunk a_next
-      if (elect_one()) {
-        mbar_arrive_expect_tx(bar_raw_full(a_as), kPatchBytesSw);
-        const ConvChunk& ak = L.chunk[a_c];
-        tma_load_4d(&L.in_map[ak.src], sA + a_as * kAStageBytes, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1,
-                    a_ty * kTileH - 1, a_b);
-      }
-      __syncwarp();
-      ++a_next;
-      if (++a_as == kAStages) { a_as = 0; a_aph ^= 1; }
-      if (++a_c == L.nchunks) {
-        a_c = 0;
-        if (++a_tx == L.tiles_x) {
-          a_tx = 0;
-          if (++a_ty == L.tiles_y) { a_ty = 0; ++a_b; }
+    // weight cursor
+    int b_k = 0, b_c = 0, b_tp0 = 0, bs = 0, bph = 0;
+    while (a_next < total || b_k < total) {
+      bool progress = false;
+      if (a_next < total) {
+        const uint32_t ok = mbar_test(bar_a_empty(a_as), a_aph ^ 1) ? 1u : 0u;
+        if (__shfl_sync(0xffffffffu, ok, 0)) {
+          if (elect_one()) {
+            const ConvChunk& ak = L.chunk[a_c];
+            const uint32_t dst = sA + a_as * kAStageBytes;
+            if (ak.gn != 0) {
+              mbar_arrive_expect_tx(bar_raw_full(a_as), kPatchBytesSw);
+              tma_load_4d(&L.in_map[ak.src], dst, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
+            } else {
+              const uint32_t bar = bar_a_full(a_as);
+              mbar_arrive_cnt(bar, kProdWarps - 1);  // stands in for the producer warps
+              if (ak.center != 0) {
+                mbar_arrive_expect_tx(bar, kTileH * kTileW * 128);
+                tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, a_tx * kTileW, a_ty * kTileH, a_b);
+              } else {
+                mbar_arrive_expect_tx(bar, kPatchBytesSw);
+                tma_load_4d(&L.in_map[ak.src], dst, bar, ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
+              }
+            }
+          }
+          __syncwarp();
+          ++a_next;
+          if (++a_as == kAStages) { a_as = 0; a_aph ^= 1; }
+          if (++a_c == L.nchunks) {
+            a_c = 0;
+            if (++a_tx == L.tiles_x) {
+              a_tx = 0;
+              if (++a_ty == L.tiles_y) { a_ty = 0; ++a_b; }
+            }
+          }
+          progress = true;
         }
       }
-    };
-    int k = 0;  // chunk counter of this CTA
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      for (int c = 0; c < L.nchunks; ++c, ++k) {
-        const ConvChunk& ck = L.chunk[c];
-        const uint8_t* w = L.weights + size_t(ck.w_off) + size_t(n_off) * 16;
-        const int ntaps = ck.ntaps;
-        if (tma_in)
-          while (a_next <= k) {
-            mbar_wait(bar_a_empty(a_as), a_aph ^ 1);
-            issue_patch();
-          }
-        for (int tp0 = 0; tp0 < ntaps; tp0 += taps_per_stage) {
-          const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
-          if (tma_in)
-            while (a_next < total && a_next < k + kAStages && mbar_test(bar_a_empty(a_as), a_aph ^ 1)) issue_patch();
-          mbar_wait(bar_b_empty(bs), bph ^ 1);
+      if (b_k < total) {
+        const uint32_t ok = mbar_test(bar_b_empty(bs), bph ^ 1) ? 1u : 0u;
+        if (__shfl_sync(0xffffffffu, ok, 0)) {
+          const ConvChunk& ck = L.chunk[b_c];
+          const uint8_t* w = L.weights + size_t(ck.w_off) + size_t(n_off) * 16;
+          const int ntaps = ck.ntaps;
+          const int g = ntaps - b_tp0 < taps_per_stage ? ntaps - b_tp0 : taps_per_stage;
           if (elect_one()) {
             const uint32_t bytes = uint32_t(g) * blob;
             mbar_arrive_expect_tx(bar_b_full(bs), bytes);  // own slice + the peers' multicast slices
             if (csize > 1) {
               const uint32_t slice = bytes / csize;
-              bulk_g2s_multicast(sB + bs * Cfg::kBStageBytes + crank * slice, w + size_t(tp0) * blob + crank * slice,
+              bulk_g2s_multicast(sB + bs * Cfg::kBStageBytes + crank * slice, w + size_t(b_tp0) * blob + crank * slice,
                                  slice, bar_b_full(bs), cmask);
             } else if (nsplit == 1) {
-              bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(tp0) * blob, bytes, bar_b_full(bs));
+              bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(b_tp0) * blob, bytes, bar_b_full(bs));
             } else {
               // this CTA's N of the n_full columns: one contiguous run per (tap, channel group)
               uint32_t dst = sB + bs * Cfg::kBStageBytes;
               for (int tg = 0; tg < g; ++tg) {
-                const uint8_t* wt = w + size_t(tp0 + tg) * gblob;
+                const uint8_t* wt = w + size_t(b_tp0 + tg) * gblob;
                 for (int cgi = 0; cgi < ncg; ++cgi, dst += N * 16)
                   bulk_g2s(dst, wt + size_t(cgi) * n_full * 16, N * 16, bar_b_full(bs));
               }
@@ -451,8 +470,16 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           }
           __syncwarp();
           if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+          b_tp0 += g;
+          if (b_tp0 >= ntaps) {
+            b_tp0 = 0;
+            ++b_k;
+            if (++b_c == L.nchunks) b_c = 0;
+          }
+          progress = true;
         }
       }
+      if (!progress) __nanosleep(32);
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // =========================================================== epilogue
@@ -751,12 +778,13 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       // tensor loads land the raw 128B-swizzled patch in the stage (out-of-image positions zero);
       // these warps apply GroupNorm + Swish in place and hand the stage to the MMA warp.  The thread
       // owns 16-byte slot (pidx & 7) of positions (pidx >> 3) + 40 i: byte pidx*16 + i*5120 of the stage
-      // (conflict-free: a warp covers 512 contiguous bytes).  Stage bases are 1024-byte aligned and 40
-      // positions are 5 swizzle periods, so the slot's logical channel group is the same for every i.
-      const int cgs = (pidx & 7) ^ ((pidx >> 3) & 7);
+      // (conflict-free: a warp covers 512 contiguous bytes).  40 positions are 5 swizzle periods, so the
+      // slot's logical channel group depends only on the stage
+      // (stage s starts 341 s = 5 s mod 8 rows into the swizzle period)
       const int pos0 = pidx >> 3;
       const int py0 = pos0 / kPatchW, px0 = pos0 - py0 * kPatchW;  // position of unit i: (py0 + 4 i, px0)
       const uint32_t smask = pos0 < kPatchPos - 8 * 40 ? 0x1ffu : 0xffu;
+      uint32_t rph = 0u;  // bit s: parity of the next phase of raw_full(s) (only GroupNorm chunks use it)
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         if (L.gn_C > 0 && b != cur_b) {
           cur_b = b;
@@ -773,9 +801,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         PROF_MARK(0);
         for (int c = 0; c < L.nchunks; ++c) {
           const ConvChunk& ck = L.chunk[c];
-          mbar_wait(bar_raw_full(as), aph);
+          if (ck.gn == 0) {  // raw chunk: the tensor load completes a_full by itself
+            if (++as == kAStages) { as = 0; aph ^= 1; }
+            continue;
+          }
+          mbar_wait(bar_raw_full(as), (rph >> as) & 1u);
+          rph ^= 1u << as;
           PROF_MARK(1);
-          if (ck.gn != 0 && !(L.dbg & 2)) {
+          if (!(L.dbg & 2)) {
+            const int cgs = (pidx & 7) ^ ((pos0 + 5 * as) & 7);
             float sc[8], sh[8];
             uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
             if (kFast) {
