@@ -116,6 +116,7 @@ struct fdsr_ctx {
   bool use_graph = true;
   bool precise = false;  // FDSR_PRECISE_SWISH=1: fp32 Swish in the producers
   bool tma_store = true; // FDSR_TMA_STORE=0: per-lane 16-byte stores in the epilogue
+  bool two_rings = true; // FDSR_TWO_RINGS=0: one patch ring of three stages for every N = 64 layer
   bool tma_in = true;    // FDSR_TMA_IN=0: producer warps gather every input patch (no TMA loads of the A operand)
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
@@ -626,6 +627,7 @@ int upload_layers(fdsr_ctx* c) {
                        c->cfg.dtype == FDSR_DTYPE_BF16, true))
         l.a_tma = 0;
     l.nchunks = int(k.chunks.size());
+    int any_center = 0;
     size_t woff = 0;
     for (int j = 0; j < l.nchunks; ++j) {
       const HChunk& ch = k.chunks[j];
@@ -639,8 +641,14 @@ int upload_layers(fdsr_ctx* c) {
       d.w_off = int(woff);
       for (int tp = 0; tp < d.ntaps; ++tp) d.tap_pos[tp] = ch.taps[tp].pos;
       d.center = (l.a_tma && ch.gn == 0 && d.ntaps == 1 && d.tap_pos[0] == kPatchW + 1) ? 1 : 0;
+      any_center += d.center;
       woff += ch.taps.size() * size_t(k.ncg) * k.N * 16;
     }
+    // patch rings (see ConvCfg): N = 64 layers with 1x1-residual chunks use 2 full + 2 centre-box stages
+    // (with three or more centre boxes per tile two 32 KB stages stall on the third: measured slower)
+    l.nR = (c->two_rings && any_center >= 1 && any_center <= 2 && l.N == 64) ? 2 : 0;
+    l.nG = l.nR ? 2 : (l.N >= 256 ? 2 : 3);
+    for (int j = 0; j < l.nchunks; ++j) l.chunk[j].ring = (l.nR && l.chunk[j].center) ? 1 : 0;
     l.gn_C = k.gn_C;
     l.gn_nsrc = k.gn_nsrc;
     l.gn_groups = c->cfg.norm_groups;
@@ -946,6 +954,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->pdl = !(e5 && e5[0] == '0');
     const char* e6 = getenv("FDSR_TMA_IN");
     c->tma_in = !(e6 && e6[0] == '0');
+    const char* e7 = getenv("FDSR_TWO_RINGS");
+    c->two_rings = !(e7 && e7[0] == '0');
   }
   if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
     delete c;

@@ -50,6 +50,7 @@ struct ConvChunk {
   int32_t vc0;        // channel offset on the virtual (concatenated) GroupNorm axis
   int32_t pix_delta;  // extra source pixel offset (parity plane of the space-to-depth view)
   int32_t ntaps;
+  int32_t ring;       // patch ring of this chunk: 0 = full stages, 1 = 32 KB centre-box stages (ConvLayer::nR > 0)
   int32_t center;     // 1: TMA-fed raw chunk whose only tap is the centre one: staged as a dense 32x8 box (no halo)
   int32_t w_off;      // byte offset of this chunk's first tap blob inside the layer's weights
   int32_t tap_pos[kMaxTaps];  // A-operand position offset of each tap (dy*kPatchW + dx)
@@ -76,6 +77,7 @@ struct ConvLayer {
   int32_t nchunks;
   int32_t ncg;          // 16-byte channel groups per chunk (8, or 2 for the 16-channel stem input)
   int32_t mode;         // ConvMode
+  int32_t nG, nR;       // patch stages in ring 0 (full) / ring 1 (centre boxes); nR = 0: single ring
   int32_t a_tma;        // 1: input patches arrive by TMA (kModeNormal, 64-channel chunks); 0: gathered by the producer warps
   int32_t B, H, W;      // output size
   int32_t N;            // MMA N of one CTA (16 / 64 / 128 / 256)

@@ -55,24 +55,34 @@ struct ConvCfg {
   static constexpr int kTmemCols =
       kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
   // a B stage holds as many consecutive tap blobs of one chunk as fit (N=64: 4 taps, 128: 2, 256: 1)
-  static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : 32768;
+  static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : (N == 64 ? 24576 : 32768);
   // N <= 128 layers are bounded by the producer/epilogue roles, not by weight streaming: give the
   // input patch a third stage (deeper decoupling of producers and MMA) and the weights two.
   // (Measured: four patch stages with four one-tap weight stages for N = 64 removes the a_full waits
   // of the GroupNorm + 1x1-residual layers but starves the MMA warp of weights: 101 -> 132 us.)
   static constexpr int kAStages = N >= 256 ? 2 : 3;
   static constexpr int kBStages = N >= 256 ? 3 : 2;
+  // N = 64 layers that mix a GroupNorm 3x3 chunk with 1x1-residual chunks split the patch memory into
+  // two rings (ConvLayer::nG / nR): two full stages for the 3x3 chunks and two 32 KB stages for the dense
+  // centre boxes.  In a single ring of three the 3x3 chunk of the next tile could only be requested two
+  // (short) chunks before it is needed, which exposed its whole load + normalise latency every tile.
+  static constexpr int kRStageBytes = kTileH * kTileW * 128;  // 32,768
+  static constexpr int kASlots = N == 64 ? 4 : kAStages;       // mbarrier sets
+  static constexpr int kABytes =
+      N == 64 ? (2 * kAStageBytes + 2 * kRStageBytes > 3 * kAStageBytes ? 2 * kAStageBytes + 2 * kRStageBytes
+                                                                        : 3 * kAStageBytes)
+              : kAStages * kAStageBytes;
   static constexpr int kNcb = N < 32 ? 1 : N / 32;
   static constexpr int kRow = N < 32 ? 32 : N;  // floats per epilogue-warp statistics row
   // shared memory carve-up (bytes)
   static constexpr int kOffA = 0;
-  static constexpr int kOffB = kOffA + kAStages * kAStageBytes;
+  static constexpr int kOffB = kOffA + kABytes;
   static constexpr int kOffTable = kOffB + kBStages * kBStageBytes;
   static constexpr int kOffGstat = kOffTable + kMaxGnC * 8;
   static constexpr int kOffBias = kOffGstat + 64 * 8;
   static constexpr int kOffTstat = kOffBias + 256 * 4;
   static constexpr int kOffBar = kOffTstat + kEpiWarps * kRow * 4;  // one row of pair sums per epilogue warp
-  static constexpr int kNumBar = 3 * kAStages + 2 * kBStages + 2 * kNumAcc;
+  static constexpr int kNumBar = 3 * kASlots + 2 * kBStages + 2 * kNumAcc;
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   // per-epilogue-warp 2 KB staging block for the TMA store of 32 px x 32 ch (64B-swizzled)
   static constexpr int kOffStage = ((kOffTmem + 16 + 1023) / 1024) * 1024;
@@ -219,7 +229,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   using Cfg = ConvCfg<N>;
   constexpr int kRow = Cfg::kRow;
-  constexpr int kAStages = Cfg::kAStages;
+  constexpr int kAStages = Cfg::kAStages;  // gathered layers: one ring of kAStages full stages
+  constexpr int kASlots = Cfg::kASlots;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -229,15 +240,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   float* tstat = reinterpret_cast<float*>(smem + Cfg::kOffTstat);
   const uint32_t bar0 = smem_u32(smem + Cfg::kOffBar);
   auto bar_a_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_a_empty = [&](int s) { return bar0 + 8u * (kAStages + s); };
-  auto bar_b_full = [&](int s) { return bar0 + 8u * (2 * kAStages + s); };
-  auto bar_b_empty = [&](int s) { return bar0 + 8u * (2 * kAStages + Cfg::kBStages + s); };
-  auto bar_acc_full = [&](int s) { return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + s); };
+  auto bar_a_empty = [&](int s) { return bar0 + 8u * (kASlots + s); };
+  auto bar_b_full = [&](int s) { return bar0 + 8u * (2 * kASlots + s); };
+  auto bar_b_empty = [&](int s) { return bar0 + 8u * (2 * kASlots + Cfg::kBStages + s); };
+  auto bar_acc_full = [&](int s) { return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + s); };
   auto bar_acc_empty = [&](int s) {
-    return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + Cfg::kNumAcc + s);
+    return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + Cfg::kNumAcc + s);
   };
   auto bar_raw_full = [&](int s) {  // TMA-fed layers: the raw patch of stage s has landed
-    return bar0 + 8u * (2 * kAStages + 2 * Cfg::kBStages + 2 * Cfg::kNumAcc + s);
+    return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + 2 * Cfg::kNumAcc + s);
   };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
   // Optional thread-block cluster of 2 CTAs (FDSR_CLUSTER=1): the CTAs walk the same layer in lock
@@ -248,7 +259,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   const uint16_t cmask = uint16_t((1u << csize) - 1u);
 
   if (tid == 0) {
-    for (int s = 0; s < kAStages; ++s) {
+    for (int s = 0; s < kASlots; ++s) {
       mbar_init(bar_a_full(s), kProdWarps);
       mbar_init(bar_a_empty(s), 1);
       mbar_init(bar_raw_full(s), 1);
@@ -304,6 +315,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       int(Cfg::kBStageBytes / blob) < kMaxTaps ? int(Cfg::kBStageBytes / blob) : kMaxTaps;
   const uint32_t sA = smem_u32(smem + Cfg::kOffA);
   const uint32_t sB = smem_u32(smem + Cfg::kOffB);
+  // patch rings: slots [0, nG) are full stages (ring 0), slots [nG, nG + nR) 32 KB centre-box stages (ring 1)
+  const int nG = L.nG, nR = L.nR;
+  auto slot_off = [&](int slot) {
+    return uint32_t(slot < nG ? slot * kAStageBytes : nG * kAStageBytes + (slot - nG) * Cfg::kRStageBytes);
+  };
 
   if (warp == 0) {
     // =========================================================== MMA issuer (whole warp converged,
@@ -325,7 +341,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const uint32_t mt1_full = uint32_t(16 * kPatchW) << pos_sh;  // second 128-row MMA tile: 16 image rows down
     const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16) + ((sB & 0x3FFFFu) >> 4);
     const int ksteps = ncg >> 1;
-    int as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
+    int gs = 0, gph = 0, rs = 0, rph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
+    // Weight stages hold taps_per_stage consecutive taps of the CTA's whole tap stream (all chunks of a
+    // tile, tile after tile), so a stage may end in the middle of a chunk and a chunk in the middle of a
+    // stage: bq = taps of the current stage already consumed.
+    int bq = 0;
     PROF_DECL;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(bar_acc_empty(acc), accph ^ 1);
@@ -335,20 +355,23 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       for (int c = 0; c < L.nchunks; ++c) {
         const ConvChunk& ck = L.chunk[c];
         const int ntaps = ck.ntaps;
-        mbar_wait(bar_a_full(as), aph);
+        const bool r1 = ck.ring != 0;
+        const int as = r1 ? nG + rs : gs;
+        mbar_wait(bar_a_full(as), r1 ? rph : gph);
         PROF_MARK(1);
-        const uint32_t a_stage = a_lo0 + as * (kAStageBytes >> 4);
+        const uint32_t a_stage = a_lo0 + (slot_off(as) >> 4);
         // centre-box chunk (raw single-tap chunk of a TMA-fed layer): dense 32x8 positions, no halo
         const bool cen = ck.center != 0;
         const uint32_t a_hi = cen ? a_hi_cen : a_hi_full;
         const uint32_t mt1 = cen ? uint32_t(16 * kTileW) << 3 : mt1_full;
-        for (int tp0 = 0; tp0 < ntaps; tp0 += taps_per_stage) {
-          const int g = ntaps - tp0 < taps_per_stage ? ntaps - tp0 : taps_per_stage;
-          mbar_wait(bar_b_full(bs), bph);
+        for (int tp0 = 0; tp0 < ntaps;) {
+          const int g = ntaps - tp0 < taps_per_stage - bq ? ntaps - tp0 : taps_per_stage - bq;
+          if (bq == 0) mbar_wait(bar_b_full(bs), bph);
           PROF_MARK(2);
           tc_fence_after();
+          const bool stage_done = bq + g == taps_per_stage;
           if (elect_one()) {
-            uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4);
+            uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4) + bq * (blob >> 4);
             for (int tg = 0; tg < g; ++tg, b_lo += blob >> 4) {
               const uint32_t a_lo = a_stage + (cen ? 0u : uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh);
               const uint32_t accum0 = (c | tp0 | tg) == 0 ? 0u : 1u;
@@ -371,16 +394,27 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                 }
               }
             }
-            if (csize > 1) umma_commit_multicast(bar_b_empty(bs), cmask);
-            else umma_commit(bar_b_empty(bs));
+            if (stage_done) {  // (the last, partial stage of the CTA is never waited for)
+              if (csize > 1) umma_commit_multicast(bar_b_empty(bs), cmask);
+              else umma_commit(bar_b_empty(bs));
+            }
             if (tp0 + g >= ntaps) umma_commit(bar_a_empty(as));
             if (tp0 + g >= ntaps && c == L.nchunks - 1) umma_commit(bar_acc_full(acc));
           }
           __syncwarp();
           PROF_MARK(3);
-          if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+          tp0 += g;
+          bq += g;
+          if (stage_done) {
+            bq = 0;
+            if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+          }
         }
-        if (++as == kAStages) { as = 0; aph ^= 1; }
+        if (r1) {
+          if (++rs == nR) { rs = 0; rph ^= 1; }
+        } else {
+          if (++gs == nG) { gs = 0; gph ^= 1; }
+        }
       }
       if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
     }
@@ -396,7 +430,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     if (tma_in) asm volatile("griddepcontrol.wait;" ::: "memory");  // patches are the previous layer's output
     const int total = (tile_end - tile_begin) * L.nchunks;
     // patch cursor
-    int a_next = tma_in ? 0 : total, a_c = 0, a_as = 0, a_aph = 0;
+    int a_next = tma_in ? 0 : total, a_c = 0, a_gs = 0, a_gph = 0, a_rs = 0, a_rph = 0;
     int a_b = tile_begin / tiles_per_img;
     int a_ty, a_tx;
     {
@@ -404,16 +438,23 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       a_ty = rem / L.tiles_x;
       a_tx = rem - a_ty * L.tiles_x;
     }
-    // weight cursor
-    int b_k = 0, b_c = 0, b_tp0 = 0, bs = 0, bph = 0;
-    while (a_next < total || b_k < total) {
+    // weight cursor: stage-loads of taps_per_stage taps over the periodic tap stream (period = taps per tile;
+    // all chunks of a layer have equally sized tap blobs, packed back to back in chunk order)
+    int taps_tile = 0;
+    for (int c = 0; c < L.nchunks; ++c) taps_tile += L.chunk[c].ntaps;
+    const int total_taps = (tile_end - tile_begin) * taps_tile;
+    int b_q = 0, b_qq = 0, bs = 0, bph = 0;  // next tap overall / inside its tile
+    const uint8_t* const w0 = L.weights + size_t(n_off) * 16;
+    while (a_next < total || b_q < total_taps) {
       bool progress = false;
       if (a_next < total) {
-        const uint32_t ok = mbar_test(bar_a_empty(a_as), a_aph ^ 1) ? 1u : 0u;
+        const bool a_r1 = L.chunk[a_c].ring != 0;
+        const int a_as = a_r1 ? nG + a_rs : a_gs;
+        const uint32_t ok = mbar_test(bar_a_empty(a_as), (a_r1 ? a_rph : a_gph) ^ 1) ? 1u : 0u;
         if (__shfl_sync(0xffffffffu, ok, 0)) {
           if (elect_one()) {
             const ConvChunk& ak = L.chunk[a_c];
-            const uint32_t dst = sA + a_as * kAStageBytes;
+            const uint32_t dst = sA + slot_off(a_as);
             if (ak.gn != 0) {
               mbar_arrive_expect_tx(bar_raw_full(a_as), kPatchBytesSw);
               tma_load_4d(&L.in_map[ak.src], dst, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
@@ -431,7 +472,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           }
           __syncwarp();
           ++a_next;
-          if (++a_as == kAStages) { a_as = 0; a_aph ^= 1; }
+          if (a_r1) {
+            if (++a_rs == nR) { a_rs = 0; a_rph ^= 1; }
+          } else {
+            if (++a_gs == nG) { a_gs = 0; a_gph ^= 1; }
+          }
           if (++a_c == L.nchunks) {
             a_c = 0;
             if (++a_tx == L.tiles_x) {
@@ -442,40 +487,38 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           progress = true;
         }
       }
-      if (b_k < total) {
+      if (b_q < total_taps) {
         const uint32_t ok = mbar_test(bar_b_empty(bs), bph ^ 1) ? 1u : 0u;
         if (__shfl_sync(0xffffffffu, ok, 0)) {
-          const ConvChunk& ck = L.chunk[b_c];
-          const uint8_t* w = L.weights + size_t(ck.w_off) + size_t(n_off) * 16;
-          const int ntaps = ck.ntaps;
-          const int g = ntaps - b_tp0 < taps_per_stage ? ntaps - b_tp0 : taps_per_stage;
+          const int g = total_taps - b_q < taps_per_stage ? total_taps - b_q : taps_per_stage;
           if (elect_one()) {
-            const uint32_t bytes = uint32_t(g) * blob;
-            mbar_arrive_expect_tx(bar_b_full(bs), bytes);  // own slice + the peers' multicast slices
-            if (csize > 1) {
-              const uint32_t slice = bytes / csize;
-              bulk_g2s_multicast(sB + bs * Cfg::kBStageBytes + crank * slice, w + size_t(b_tp0) * blob + crank * slice,
-                                 slice, bar_b_full(bs), cmask);
-            } else if (nsplit == 1) {
-              bulk_g2s(sB + bs * Cfg::kBStageBytes, w + size_t(b_tp0) * blob, bytes, bar_b_full(bs));
+            mbar_arrive_expect_tx(bar_b_full(bs), uint32_t(g) * blob);  // own slices + the peers' multicast slices
+            const uint32_t dst0 = sB + bs * Cfg::kBStageBytes;
+            if (csize == 1 && nsplit == 1) {
+              const int first = g < taps_tile - b_qq ? g : taps_tile - b_qq;  // up to the end of the tile's taps
+              bulk_g2s(dst0, w0 + size_t(b_qq) * blob, uint32_t(first) * blob, bar_b_full(bs));
+              if (first < g) bulk_g2s(dst0 + uint32_t(first) * blob, w0, uint32_t(g - first) * blob, bar_b_full(bs));
             } else {
-              // this CTA's N of the n_full columns: one contiguous run per (tap, channel group)
-              uint32_t dst = sB + bs * Cfg::kBStageBytes;
+              int qq = b_qq;
               for (int tg = 0; tg < g; ++tg) {
-                const uint8_t* wt = w + size_t(b_tp0 + tg) * gblob;
-                for (int cgi = 0; cgi < ncg; ++cgi, dst += N * 16)
-                  bulk_g2s(dst, wt + size_t(cgi) * n_full * 16, N * 16, bar_b_full(bs));
+                const uint8_t* wt = w0 + size_t(qq) * gblob;
+                const uint32_t dst = dst0 + uint32_t(tg) * blob;
+                if (csize > 1) {
+                  const uint32_t slice = blob / csize;
+                  bulk_g2s_multicast(dst + crank * slice, wt + crank * slice, slice, bar_b_full(bs), cmask);
+                } else {
+                  // this CTA's N of the n_full columns: one contiguous run per channel group
+                  for (int cgi = 0; cgi < ncg; ++cgi)
+                    bulk_g2s(dst + uint32_t(cgi) * N * 16, wt + size_t(cgi) * n_full * 16, N * 16, bar_b_full(bs));
+                }
+                if (++qq == taps_tile) qq = 0;
               }
             }
           }
           __syncwarp();
           if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
-          b_tp0 += g;
-          if (b_tp0 >= ntaps) {
-            b_tp0 = 0;
-            ++b_k;
-            if (++b_c == L.nchunks) b_c = 0;
-          }
+          b_q += g;
+          b_qq = (b_qq + g) % taps_tile;
           progress = true;
         }
       }
@@ -525,6 +568,20 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       if (has_res) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + k, valid);
+        // pull this lane's residual row of the NEXT tile into L2 while this tile is drained (the loads
+        // above then mostly hit L2 instead of exposing HBM latency on the epilogue's critical path)
+        int ntx = tx + 1, nty = ty, nb = b;
+        if (ntx == tiles_x) {
+          ntx = 0;
+          if (++nty == L.tiles_y) { nty = 0; ++nb; }
+        }
+        const int nx = ntx * kTileW + r, ny = nty * kTileH + mt * 16 + g;
+        if (tile + 1 < tile_end && ny < H && nx < W) {
+          const uint8_t* np = reinterpret_cast<const uint8_t*>(L.resid) +
+                              (size_t(uint32_t((nb * H + ny) * W + nx)) * n_full + n_off) * 2;
+#pragma unroll
+          for (int k = 0; k < N * 2; k += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + k));
+        }
       }
       mbar_wait(bar_acc_full(acc), accph);
       PROF_MARK(0);
@@ -802,7 +859,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         for (int c = 0; c < L.nchunks; ++c) {
           const ConvChunk& ck = L.chunk[c];
           if (ck.gn == 0) {  // raw chunk: the tensor load completes a_full by itself
-            if (++as == kAStages) { as = 0; aph ^= 1; }
+            if (ck.ring == 0 && ++as == nG) as = 0;
             continue;
           }
           mbar_wait(bar_raw_full(as), (rph >> as) & 1u);
@@ -823,7 +880,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                 sh[j] = e.y;
               }
             }
-            const uint32_t a0 = sA + as * kAStageBytes + uint32_t(pidx) * 16;
+            const uint32_t a0 = sA + as * kAStageBytes + uint32_t(pidx) * 16;  // (GroupNorm chunks: ring 0)
             uint4 rv[kMaxUnits];
 #pragma unroll
             for (int i = 0; i < kMaxUnits; ++i)
@@ -836,7 +893,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           PROF_MARK(3);
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_full(as));
-          if (++as == kAStages) { as = 0; aph ^= 1; }
+          if (++as == nG) as = 0;
         }
         if (++tx == tiles_x) {
           tx = 0;
