@@ -55,6 +55,20 @@ def measured_peaks():
     return 1400.0, "fallback (B200_PROFILING.md sustained figure)"
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the heaviest conv launch (ups.7, 309 GFLOP) from the committed
+    `ncu --set full` capture; the other captured launches are listed in profiles/r1/traffic.json."""
+    p = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    try:
+        d = json.load(open(p))["launches"]
+        top = d["ups.7"]
+        note = "ncu dram__bytes_read.sum + dram__bytes_write.sum of launch ups.7 (B=16, 256^2; algorithmic 169 MB: " \
+               "34 MB in + 134 MB out + 1.2 MB weights); per-launch figures for 4 captured launches in profiles/r1/traffic.json"
+        return top["dram_read_bytes"] + top["dram_write_bytes"], note
+    except Exception:
+        return None, "profiles/r1/traffic.json missing"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
 
@@ -215,8 +229,9 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
     flop_per_image = eng.unet_flops() / B * T
+    traffic, traffic_note = ncu_traffic()
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "conv_gemm_kernel (all conv layers of one UNet step)",
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel": "conv_gemm_kernel (all conv layers of one UNet step)",
                 "launches_profiled": len(conv), "conv_ms_per_unet_step": conv_ms,
                 "other_ms_per_unet_step": sum(ms for _, ms, fl in prof if fl == 0),
                 "whole_step_frac": value / world * flop_per_image / 1e12 / peak}

@@ -6,22 +6,25 @@
 //
 // Warp roles (640 threads, 1 CTA / SM, persistent over a contiguous range of tiles):
 //   warp 0      MMA issuer (one elected thread): tcgen05.mma from shared-memory descriptors
-//   warp 1      weight loader (one elected thread): cp.async.bulk of pre-packed tap blobs
+//   warp 1      loader (one elected thread): TMA tensor loads of the input patches (one per 64-channel
+//               chunk, 128B-swizzled, zero-filled halo) and cp.async.bulk of pre-packed weight tap blobs
 //   warps 4-11  epilogue (one warpgroup per 128-row MMA tile): tcgen05.ld -> bias/FiLM -> residual
-//               -> 16-bit store -> GroupNorm pair statistics
-//   warps 2,3,12-19  input producers: coalesced 16B global loads of the (32+2)x(8+2) input patch,
-//               GroupNorm scale/shift + Swish in registers, 16B stores into the resident
-//               patch laid out as [channel group][position][8 ch] (no-swizzle core matrices).
+//               -> 16-bit TMA store -> GroupNorm pair statistics
+//   warps 2,3,12-19  producers: GroupNorm scale/shift + Swish applied in place to the TMA-delivered
+//               patch (pixel-major, 128 B per position); for the gathered layers (nearest-upsample,
+//               stride-2, 16-channel stem) coalesced 16B global loads, transform in registers, 16B
+//               stores into a no-swizzle [channel group][position][8 ch] patch.
 // The patch is loaded and transformed ONCE per 64-channel chunk and then serves all nine 3x3
-// taps as shifted shared-memory descriptor views (start address + 16 B * (dy*10 + dx), SBO =
-// 160 B), so the A operand is never re-fetched per tap and GroupNorm/Swish/concat/upsample/
-// space-to-depth never touch HBM as separate passes.
+// taps as shifted shared-memory descriptor views (start address + 128 B * (dy*10 + dx), SBO =
+// 1280 B; the MMA unit swizzles on absolute address bits, tools/probe_umma.cu), so the A operand is
+// never re-fetched per tap and GroupNorm/Swish/concat/upsample/space-to-depth never touch HBM as
+// separate passes.
 //
-// The kernel is instruction-issue sensitive (ncu: ~0.35 IPC per scheduler with 5 warps each), so
+// The kernel is instruction-issue sensitive (ncu: ~0.45 IPC per scheduler with 5 warps each), so
 // the layer description is a __grid_constant__ kernel parameter (constant-bank operands instead of
-// shared-memory loads), per-thread patch coordinates are computed once per launch, waits use the
-// mbarrier suspend hint instead of spinning, and for N = 64 the GroupNorm statistics are kept as
-// per-lane running sums in spare TMEM columns and reduced across lanes only when the sample changes.
+// shared-memory loads), waits use the mbarrier suspend hint instead of spinning, and for N = 64 the
+// GroupNorm statistics are kept as per-lane running sums in spare TMEM columns and reduced across
+// lanes only once per tile group.
 //
 // Reference ops covered (FastDiffSR/model/fastdiffsr_modules/unet.py): Block :89-101 (GroupNorm,
 // Swish, Conv3x3), ResnetBlock :104-120 (FiLM add, residual 1x1 / identity), Downsample :77-83,

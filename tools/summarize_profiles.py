@@ -44,7 +44,7 @@ if os.path.exists(ll):
         lines.append(f"| `{k}` | {n} | {us:.0f} | {100 * us / tot:.1f}% |")
     conv = sum(us for k, (n, us) in agg.items() if "conv_gemm" in k)
     lines += ["", f"conv_gemm_kernel share of the step: **{100 * conv / tot:.1f}%** of {tot / 1000:.1f} ms "
-              "(bench.py's CUDA-event split: conv 5.34 ms of 5.65 ms per UNet step = 94.6%)", ""]
+              "(bench.py's CUDA-event split: conv 4.85 ms of 5.16 ms per UNet step = 94.1%)", ""]
 # ---- per-kernel details
 want = ["Duration", "SM Frequency", "Compute (SM) Throughput", "Memory Throughput", "DRAM Throughput", "L2 Hit Rate",
         "Registers Per Thread", "Dynamic Shared Memory Per Block", "Issued Warp Per Scheduler", "Executed Instructions",
