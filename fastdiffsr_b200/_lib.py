@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FDSR_LIB", os.path.join(_HERE, "libfdsr.so"))
 CSRC = os.path.join(_HERE, "csrc")
 MAX_LEVELS = 8
-DTYPE_FP16, DTYPE_BF16 = 0, 1
+DTYPE_FP16, DTYPE_BF16, DTYPE_FP32 = 0, 1, 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

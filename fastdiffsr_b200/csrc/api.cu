@@ -15,6 +15,7 @@
 #include "../../include/fdsr.h"
 #include "aux_kernels.cuh"
 #include "conv_kernel.cuh"
+#include "conv_f32.cuh"
 
 using namespace fdsr;
 
@@ -97,6 +98,12 @@ struct fdsr_ctx {
   size_t off_cond = 0, off_x = 0, off_eps = 0, off_sr = 0, off_psum = 0, off_pmax = 0, off_gate = 0,
          off_sp = 0, off_seed = 0;
   std::vector<ConvLayer> h_layers;  // passed by value as __grid_constant__ kernel parameters
+  std::vector<F32Layer> f_layers;   // fp32 parity mode: the same plan for conv_f32_kernel
+  std::vector<F32GnArgs> f_gn;
+  float* d_weights32 = nullptr;     // fp32 parity mode weights: per conv, per chunk [tap][ci][N]
+  std::vector<size_t> w32_off;      // per conv (floats)
+  size_t off_gntab = 0;             // [B][kMaxGnC] float2 scratch of the fp32 mode
+  int esize() const { return cfg.dtype == FDSR_DTYPE_FP32 ? 4 : 2; }
   long long* d_prof = nullptr;  // role cycle counters (FDSR_PROFILE builds)
   bool layers_dirty = true;
   // bicubic tables (cached per size pair)
@@ -438,6 +445,41 @@ int pack_weights(fdsr_ctx* c) {
   return FDSR_OK;
 }
 
+// fp32 parity mode: per conv, per chunk: [tap][ci < creal][N] floats
+int pack_weights_f32(fdsr_ctx* c) {
+  size_t total = 0;
+  c->w32_off.assign(c->convs.size(), 0);
+  for (size_t i = 0; i < c->convs.size(); ++i) {
+    c->w32_off[i] = total;
+    for (const HChunk& ch : c->convs[i].chunks) total += ch.taps.size() * size_t(ch.creal) * c->convs[i].N;
+  }
+  std::vector<float> host(total, 0.f);
+  for (size_t i = 0; i < c->convs.size(); ++i) {
+    const HConv& k = c->convs[i];
+    size_t off = c->w32_off[i];
+    for (const HChunk& ch : k.chunks) {
+      const std::vector<float>* w = find_w(c, ch.wname);
+      if (!w) return fail(c, FDSR_E_NOTFOUND, "missing weight %s", ch.wname.c_str());
+      const bool is1x1 = ch.wname.find("res_conv") != std::string::npos;
+      const int kk = is1x1 ? 1 : 3;
+      const size_t cin_w = w->size() / (size_t(k.cout) * kk * kk);
+      for (const HTap& tp : ch.taps) {
+        for (int ci = 0; ci < ch.creal; ++ci)
+          for (int n = 0; n < k.cout; ++n)
+            host[off + size_t(ci) * k.N + n] =
+                (*w)[((size_t(n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk + (is1x1 ? 0 : tp.kx)];
+        off += size_t(ch.creal) * k.N;
+      }
+    }
+  }
+  if (c->d_weights32) cudaFree(c->d_weights32);
+  c->d_weights32 = nullptr;
+  CUDA_TRY(c, cudaMalloc(&c->d_weights32, total * 4 + 16));
+  CUDA_TRY(c, cudaMemcpy(c->d_weights32, host.data(), total * 4, cudaMemcpyHostToDevice));
+  c->weights_bytes = total * 4;
+  return FDSR_OK;
+}
+
 int upload_params(fdsr_ctx* c) {
   std::vector<float> p;
   for (HConv& k : c->convs) {
@@ -585,7 +627,102 @@ bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bo
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 parity mode: layer descriptions for conv_f32_kernel / f32_gn_table_kernel
+int upload_layers_f32(fdsr_ctx* c) {
+  const int B = c->B, H = c->H, W = c->W;
+  c->f_layers.assign(c->convs.size(), F32Layer{});
+  c->f_gn.assign(c->convs.size(), F32GnArgs{});
+  for (size_t i = 0; i < c->convs.size(); ++i) {
+    const HConv& k = c->convs[i];
+    F32Layer& l = c->f_layers[i];
+    memset(&l, 0, sizeof l);
+    const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
+    l.B = B;
+    l.H = H >> lvl;
+    l.W = W >> lvl;
+    l.N = k.N;
+    l.mode = k.mode;
+    l.nchunks = int(k.chunks.size());
+    size_t woff = c->w32_off[i];
+    for (int j = 0; j < l.nchunks; ++j) {
+      const HChunk& ch = k.chunks[j];
+      const HTensor& t = c->tensors[k.src[ch.slot]];
+      F32Chunk& d = l.chunk[j];
+      d.src = reinterpret_cast<const float*>(c->d_ws + t.off);
+      d.C = t.C;
+      d.H = H >> t.level;
+      d.W = W >> t.level;
+      d.c0 = ch.c0;
+      d.nch = ch.creal;
+      d.gn = ch.gn;
+      d.vc0 = ch.vc0;
+      d.pa = ch.parity < 0 ? 0 : (ch.parity >> 1);
+      d.pb = ch.parity < 0 ? 0 : (ch.parity & 1);
+      d.ntaps = int(ch.taps.size());
+      for (int tp = 0; tp < d.ntaps; ++tp) {
+        d.dy[tp] = int8_t(ch.taps[tp].pos / kPatchW - 1);
+        d.dx[tp] = int8_t(ch.taps[tp].pos % kPatchW - 1);
+      }
+      d.w_off = int32_t(woff - c->w32_off[i]);
+      woff += ch.taps.size() * size_t(ch.creal) * k.N;
+    }
+    l.gn_C = k.gn_C;
+    l.gn_tab = reinterpret_cast<const float2*>(c->d_ws + c->off_gntab);
+    l.weights = c->d_weights32 + c->w32_off[i];
+    l.bias = c->d_bias + k.bias_off;
+    l.bias_tstride = k.N;
+    l.resid = k.resid >= 0 ? reinterpret_cast<const float*>(c->d_ws + c->tensors[k.resid].off) : nullptr;
+    l.out_mode = k.out_mode;
+    l.out_c = k.out_c;
+    if (k.out_mode == kOutAct) {
+      const HTensor& t = c->tensors[k.out];
+      l.out = reinterpret_cast<float*>(c->d_ws + t.off);
+      l.out_stats = t.stats ? reinterpret_cast<unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
+    } else {
+      l.out = reinterpret_cast<float*>(c->d_ws + c->off_eps);
+    }
+    if (k.gn_C) {
+      F32GnArgs& g = c->f_gn[i];
+      for (int s2 = 0; s2 < k.gn_nsrc && s2 < 2; ++s2) {
+        const HTensor& t = c->tensors[k.src[s2]];
+        g.stats[s2] = reinterpret_cast<const unsigned long long*>(c->d_ws + t.stats_off);
+        g.C[s2] = t.C;
+      }
+      if (k.gn_nsrc == 1) {
+        g.stats[1] = g.stats[0];
+        g.C[1] = 0;
+      }
+      const HTensor& t0 = c->tensors[k.src[0]];
+      g.gn_C = k.gn_C;
+      g.groups = c->cfg.norm_groups;
+      g.HW = (H >> t0.level) * (W >> t0.level);
+      g.eps = 1e-5f;
+      g.gamma = c->d_params + k.gamma_off;
+      g.beta = c->d_params + k.gamma_off + k.gn_C;
+      g.tab = reinterpret_cast<float2*>(c->d_ws + c->off_gntab);
+    }
+  }
+  static_assert(sizeof(F32Layer) <= 4000, "F32Layer must fit the kernel parameter space");
+  c->layers_dirty = false;
+  return FDSR_OK;
+}
+
+int launch_conv_f32(fdsr_ctx* c, int li, int t, cudaStream_t st) {
+  const HConv& k = c->convs[li];
+  const F32Layer& l = c->f_layers[li];
+  if (k.gn_C) {
+    f32_gn_table_kernel<<<c->B, 256, 0, st>>>(c->f_gn[li]);
+    ++c->launches;
+  }
+  const int tiles = c->B * ((l.W + kF32Tile - 1) / kF32Tile) * ((l.H + kF32Tile - 1) / kF32Tile);
+  conv_f32_kernel<<<dim3(tiles, (l.N + kF32NBlk - 1) / kF32NBlk), 256, 0, st>>>(l, t);
+  CUDA_TRY(c, cudaGetLastError());
+  ++c->launches;
+  return FDSR_OK;
+}
+
 int upload_layers(fdsr_ctx* c) {
+  if (c->cfg.dtype == FDSR_DTYPE_FP32) return upload_layers_f32(c);
   const int B = c->B, H = c->H, W = c->W;
   if (!c->d_prof) {
     CUDA_TRY(c, cudaMalloc(&c->d_prof, size_t(c->num_sms) * 32 * 8));
@@ -712,6 +849,9 @@ cudaError_t set_conv_attrs() {
   return e;
 }
 
+template <typename T>
+int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st);
+
 template <int N, typename T>
 int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
   const int ngroups = ntiles / c->h_layers[li].group;
@@ -746,6 +886,12 @@ int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
 
 template <typename T>
 int launch_conv(fdsr_ctx* c, int li, int t, cudaStream_t st) {
+  if constexpr (sizeof(T) == 4) return launch_conv_f32(c, li, t, st);
+  else return launch_conv16<T>(c, li, t, st);
+}
+
+template <typename T>
+int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st) {
   const HConv& k = c->convs[li];
   const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
   const int h = c->H >> lvl, w = c->W >> lvl;
@@ -805,6 +951,7 @@ int unet_internal(fdsr_ctx* c, int t, cudaStream_t st) {
 }
 
 int unet_dispatch(fdsr_ctx* c, int t, cudaStream_t st) {
+  if (c->cfg.dtype == FDSR_DTYPE_FP32) return unet_internal<float>(c, t, st);
   return c->cfg.dtype == FDSR_DTYPE_BF16 ? unet_internal<__nv_bfloat16>(c, t, st) : unet_internal<__half>(c, t, st);
 }
 
@@ -957,9 +1104,9 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     const char* e7 = getenv("FDSR_TWO_RINGS");
     c->two_rings = !(e7 && e7[0] == '0');
   }
-  if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16) {
+  if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16 && cfg->dtype != FDSR_DTYPE_FP32) {
     delete c;
-    return fail(nullptr, FDSR_E_INVALID, "dtype must be FDSR_DTYPE_FP16 or FDSR_DTYPE_BF16");
+    return fail(nullptr, FDSR_E_INVALID, "dtype must be FDSR_DTYPE_FP16, FDSR_DTYPE_BF16 or FDSR_DTYPE_FP32");
   }
   const int rc = build_plan(c);
   if (rc) {
@@ -967,8 +1114,9 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     delete c;
     return rc;
   }
-  const cudaError_t ae =
-      cfg->dtype == FDSR_DTYPE_BF16 ? set_conv_attrs<__nv_bfloat16>() : set_conv_attrs<__half>();
+  const cudaError_t ae = cfg->dtype == FDSR_DTYPE_FP32 ? cudaSuccess
+                         : cfg->dtype == FDSR_DTYPE_BF16 ? set_conv_attrs<__nv_bfloat16>()
+                                                         : set_conv_attrs<__half>();
   if (ae != cudaSuccess) {
     delete c;
     return fail(nullptr, FDSR_E_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ae));
@@ -981,6 +1129,7 @@ int fdsr_destroy(fdsr_ctx* c) {
   if (!c) return FDSR_OK;
   if (c->graph) cudaGraphExecDestroy(c->graph);
   cudaFree(c->d_weights);
+  cudaFree(c->d_weights32);
   cudaFree(c->d_params);
   cudaFree(c->d_bias);
   cudaFree(c->d_ws);
@@ -1011,7 +1160,8 @@ int fdsr_load_weights(fdsr_ctx* c, const char* const* names, const float* const*
       if (w->size() % (size_t(k.cout) * (is1x1 ? 1 : 9)) != 0)
         return fail(c, FDSR_E_INVALID, "unexpected size for %s", ch.wname.c_str());
     }
-  int rc = c->cfg.dtype == FDSR_DTYPE_BF16 ? pack_weights<__nv_bfloat16>(c) : pack_weights<__half>(c);
+  int rc = c->cfg.dtype == FDSR_DTYPE_FP32 ? pack_weights_f32(c)
+           : c->cfg.dtype == FDSR_DTYPE_BF16 ? pack_weights<__nv_bfloat16>(c) : pack_weights<__half>(c);
   if (rc) return rc;
   rc = upload_params(c);
   if (rc) return rc;
@@ -1094,7 +1244,7 @@ int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
   size_t off = 0;
   for (HTensor& t : c->tensors) {
     t.off = off;
-    off = align_up(off + size_t(B) * (H >> t.level) * (W >> t.level) * t.C * 2, 256);
+    off = align_up(off + size_t(B) * (H >> t.level) * (W >> t.level) * t.C * c->esize(), 256);
   }
   c->stats_off = off;
   for (HTensor& t : c->tensors)
@@ -1129,6 +1279,8 @@ int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
   off += img;
   c->off_seed = off;
   off += 256;
+  c->off_gntab = off;
+  off += c->cfg.dtype == FDSR_DTYPE_FP32 ? size_t(B) * kMaxGnC * 8 : 0;
   if (c->d_ws) cudaFree(c->d_ws);
   c->d_ws = nullptr;
   CUDA_TRY(c, cudaMalloc(&c->d_ws, off));
@@ -1234,7 +1386,8 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
     CUDA_TRY(c, cudaGraphLaunch(c->graph, st));
     // launches per replay: recompute deterministically
     int per_unet = 1;
-    for (const HOp& op : c->ops) per_unet += op.kind == 0 ? 1 : 4;
+    for (const HOp& op : c->ops)
+      per_unet += op.kind != 0 ? 4 : ((c->cfg.dtype == FDSR_DTYPE_FP32 && c->convs[op.idx].gn_C) ? 2 : 1);
     c->launches += int64_t(c->T) * (per_unet + 1) + 1 + (noise ? 0 : 1) + (trace ? fdsr_trace_frames(c) : 0);
   } else {
     rc = sample_enqueue(c, noise, trace, st);
@@ -1335,7 +1488,10 @@ int fdsr_debug_read_tensor(fdsr_ctx* c, const char* name, float* out, int64_t ca
       const int64_t n = int64_t(c->B) * h * w * t.C;
       if (cap < n) return fail(c, FDSR_E_INVALID, "capacity too small (%lld needed)", (long long)n);
       cudaStream_t st = static_cast<cudaStream_t>(stream);
-      if (c->cfg.dtype == FDSR_DTYPE_BF16)
+      if (c->cfg.dtype == FDSR_DTYPE_FP32)
+        nhwc_to_nchw_kernel<float><<<unsigned((n + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float*>(c->d_ws + t.off), out, c->B, h * w, t.C);
+      else if (c->cfg.dtype == FDSR_DTYPE_BF16)
         nhwc_to_nchw_kernel<__nv_bfloat16><<<unsigned((n + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const __nv_bfloat16*>(c->d_ws + t.off), out, c->B, h * w, t.C);
       else
@@ -1379,13 +1535,14 @@ int fdsr_debug_profile_unet(fdsr_ctx* c, int32_t t, int32_t reps, float* ms_out_
   }
   std::vector<cudaEvent_t> ev(size_t(nops) * 2 * reps);
   for (auto& e : ev) CUDA_TRY(c, cudaEventCreate(&e));
-  const bool bf = c->cfg.dtype == FDSR_DTYPE_BF16;
+  const bool bf = c->cfg.dtype == FDSR_DTYPE_BF16, f32 = c->cfg.dtype == FDSR_DTYPE_FP32;
   for (int r = 0; r < reps; ++r) {
     CUDA_TRY(c, cudaMemsetAsync(c->d_ws + c->stats_off, 0, c->stats_bytes, st));
     for (int i = 0; i < nops; ++i) {
       const HOp& op = c->ops[i];
       CUDA_TRY(c, cudaEventRecord(ev[(size_t(r) * nops + i) * 2], st));
-      if (op.kind == 0) rc = bf ? launch_conv<__nv_bfloat16>(c, op.idx, t, st) : launch_conv<__half>(c, op.idx, t, st);
+      if (f32) rc = op.kind == 0 ? launch_conv<float>(c, op.idx, t, st) : launch_attn<float>(c, c->attns[op.idx], st);
+      else if (op.kind == 0) rc = bf ? launch_conv<__nv_bfloat16>(c, op.idx, t, st) : launch_conv<__half>(c, op.idx, t, st);
       else rc = bf ? launch_attn<__nv_bfloat16>(c, c->attns[op.idx], st) : launch_attn<__half>(c, c->attns[op.idx], st);
       if (rc) return rc;
       CUDA_TRY(c, cudaEventRecord(ev[(size_t(r) * nops + i) * 2 + 1], st));
@@ -1411,6 +1568,7 @@ int fdsr_debug_role_cycles(fdsr_ctx* c, int32_t op, int32_t t, int64_t* out_host
   if (rc) return rc;
   if (!c->d_ws) return fail(c, FDSR_E_STATE, "run a forward first");
   if (op < 0 || op >= int(c->ops.size()) || c->ops[op].kind != 0) return fail(c, FDSR_E_INVALID, "op is not a conv");
+  if (c->cfg.dtype == FDSR_DTYPE_FP32) return fail(c, FDSR_E_INVALID, "role cycles exist for the tensor-core kernel only");
   const int n = c->num_sms * 32;
   if (cap < n) return fail(c, FDSR_E_INVALID, "capacity too small");
   if (c->layers_dirty) {

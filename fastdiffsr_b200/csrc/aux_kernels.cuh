@@ -51,6 +51,18 @@ __global__ void noise_fill_kernel(float* __restrict__ out, int64_t n4, const uin
 // Input assembly: cat([cond, x_t], 1) (diffusion.py:173) as a 16-channel NHWC 16-bit tensor
 // (channels 0-2 cond, 3-5 x_t, 6-15 zero) feeding the stem conv as a single 16-wide K chunk.
 // ------------------------------------------------------------------------------------------
+// Two consecutive channels of an activation tensor (16-bit packed pair, or two floats in fp32 mode)
+template <typename T>
+__device__ __forceinline__ float2 ld_pair(const T* p) {
+  if constexpr (sizeof(T) == 4) return *reinterpret_cast<const float2*>(p);
+  else return Cvt<T>::unpack(*reinterpret_cast<const uint32_t*>(p));
+}
+template <typename T>
+__device__ __forceinline__ void st_pair(T* p, float a, float b) {
+  if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(p) = make_float2(a, b);
+  else *reinterpret_cast<uint32_t*>(p) = Cvt<T>::pack(a, b);
+}
+
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ cond, const float* __restrict__ x,
                                   T* __restrict__ out, int B, int HW) {
@@ -60,14 +72,22 @@ __global__ void pack_input_kernel(const float* __restrict__ cond, const float* _
   const int p = int(i - int64_t(b) * HW);
   const float* cp = cond + int64_t(b) * 3 * HW + p;
   const float* xp = x + int64_t(b) * 3 * HW + p;
-  uint4 lo, hi = make_uint4(0u, 0u, 0u, 0u);
-  lo.x = Cvt<T>::pack(cp[0], cp[HW]);
-  lo.y = Cvt<T>::pack(cp[2 * HW], xp[0]);
-  lo.z = Cvt<T>::pack(xp[HW], xp[2 * HW]);
-  lo.w = 0u;
-  uint4* o = reinterpret_cast<uint4*>(out + i * 16);
-  o[0] = lo;
-  o[1] = hi;
+  if constexpr (sizeof(T) == 4) {
+    float4* o = reinterpret_cast<float4*>(out + i * 16);
+    o[0] = make_float4(cp[0], cp[HW], cp[2 * HW], xp[0]);
+    o[1] = make_float4(xp[HW], xp[2 * HW], 0.f, 0.f);
+    o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    uint4 lo, hi = make_uint4(0u, 0u, 0u, 0u);
+    lo.x = Cvt<T>::pack(cp[0], cp[HW]);
+    lo.y = Cvt<T>::pack(cp[2 * HW], xp[0]);
+    lo.z = Cvt<T>::pack(xp[HW], xp[2 * HW]);
+    lo.w = 0u;
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = lo;
+    o[1] = hi;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -135,9 +155,9 @@ __global__ void clam_pool_kernel(const T* __restrict__ x, unsigned long long* __
   const int p1 = min(p0 + pix_per_block, HW);
   for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
     float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
-    const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + (int64_t(b) * HW + p0) * C) + c2;
-    for (int p = p0; p < p1; ++p, xp += C / 2) {
-      const float2 f = Cvt<T>::unpack(*xp);
+    const T* xp = x + (int64_t(b) * HW + p0) * C + 2 * c2;
+    for (int p = p0; p < p1; ++p, xp += C) {
+      const float2 f = ld_pair<T>(xp);
       s0 += f.x;
       s1 += f.y;
       m0 = fmaxf(m0, f.x);
@@ -193,11 +213,11 @@ __global__ void slam_pool_kernel(const T* __restrict__ x, const float* __restric
   const int lane = threadIdx.x & 31;
   if (wid >= int64_t(B) * HW) return;
   const int b = int(wid / HW);
-  const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + wid * C);
+  const T* xp = x + wid * C;
   const float* g = gate + b * C;
   float s = 0.f, m = -INFINITY;
   for (int c2 = lane; c2 < C / 2; c2 += 32) {
-    const float2 f = Cvt<T>::unpack(xp[c2]);
+    const float2 f = ld_pair<T>(xp + 2 * c2);
     const float a = f.x * g[2 * c2], c = f.y * g[2 * c2 + 1];
     s += a + c;
     m = fmaxf(m, fmaxf(a, c));
@@ -235,13 +255,13 @@ __global__ void slam_apply_kernel(const T* __restrict__ x, const float* __restri
     }
     for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     const float sg = 1.0f / (1.0f + expf(-a));
-    const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + (int64_t(b) * HW + p) * C);
-    uint32_t* op = reinterpret_cast<uint32_t*>(out + (int64_t(b) * HW + p) * C);
+    const T* xp = x + (int64_t(b) * HW + p) * C;
+    T* op = out + (int64_t(b) * HW + p) * C;
     const float* g = gate + b * C;
     for (int c2 = lane; c2 < C / 2; c2 += 32) {
-      const float2 f = Cvt<T>::unpack(xp[c2]);
+      const float2 f = ld_pair<T>(xp + 2 * c2);
       const float u = sg * (g[2 * c2] * f.x), v = sg * (g[2 * c2 + 1] * f.y);
-      op[c2] = Cvt<T>::pack(u, v);
+      st_pair<T>(op + 2 * c2, u, v);
       row[2 * c2] = u + v;
       row[2 * c2 + 1] = u * u + v * v;
     }
@@ -355,7 +375,8 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict_
   const int b = int(bp / HW);
   const int p = int(bp - int64_t(b) * HW);
   float v;
-  if constexpr (Cvt<T>::kFmt == 0) v = __half2float(in[i]);
+  if constexpr (sizeof(T) == 4) v = in[i];
+  else if constexpr (Cvt<T>::kFmt == 0) v = __half2float(in[i]);
   else v = __bfloat162float(in[i]);
   out[(int64_t(b) * C + c) * HW + p] = v;
 }

@@ -10,7 +10,8 @@ import torch
 from . import _lib
 from ._lib import FdsrConfig, FdsrError
 
-_DTYPES = {"fp16": _lib.DTYPE_FP16, "float16": _lib.DTYPE_FP16, "bf16": _lib.DTYPE_BF16, "bfloat16": _lib.DTYPE_BF16}
+_DTYPES = {"fp16": _lib.DTYPE_FP16, "float16": _lib.DTYPE_FP16, "bf16": _lib.DTYPE_BF16, "bfloat16": _lib.DTYPE_BF16,
+           "fp32": _lib.DTYPE_FP32, "float32": _lib.DTYPE_FP32}  # fp32 = CUDA-core parity mode (slow)
 
 
 def _ptr(t):
