@@ -114,6 +114,8 @@ struct fdsr_ctx {
   std::vector<BicTab> bic;
   uint8_t* d_bic_tmp = nullptr;
   size_t bic_tmp_bytes = 0;
+  unsigned long long* d_metric = nullptr;  // [B][4] integer accumulators of fdsr_metrics_u8
+  size_t metric_bytes = 0;
   // pinned staging for the host-buffer path
   uint8_t* h_pin = nullptr;
   size_t h_pin_bytes = 0;
@@ -1135,6 +1137,7 @@ int fdsr_destroy(fdsr_ctx* c) {
   cudaFree(c->d_ws);
   cudaFree(c->d_prof);
   cudaFree(c->d_bic_tmp);
+  cudaFree(c->d_metric);
   cudaFree(c->d_stage);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   for (auto& b : c->bic) {
@@ -1470,6 +1473,25 @@ int fdsr_sse_u8(fdsr_ctx* c, const float* a, const float* b, int32_t B, int32_t 
   sse_u8_kernel<<<dim3(gx > 0 ? gx : 1, B), 256, 0, st>>>(a, b, sse, per);
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
+  return FDSR_OK;
+}
+
+int fdsr_metrics_u8(fdsr_ctx* c, const float* a, const float* b, int32_t B, int32_t H, int32_t W, double ergas_scale,
+                    double* out, void* stream) {
+  if (!c || !a || !b || !out || B < 1 || H < 1 || W < 1) return fail(c, FDSR_E_INVALID, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (size_t(B) * 32 > c->metric_bytes) {
+    cudaFree(c->d_metric);
+    c->d_metric = nullptr;
+    CUDA_TRY(c, cudaMalloc(&c->d_metric, size_t(B) * 32));
+    c->metric_bytes = size_t(B) * 32;
+  }
+  CUDA_TRY(c, cudaMemsetAsync(c->d_metric, 0, size_t(B) * 32, st));
+  metrics_u8_kernel<<<dim3((W + kSsimTile - 1) / kSsimTile, (H + kSsimTile - 1) / kSsimTile, B * 3), 256, 0, st>>>(
+      a, b, c->d_metric, H, W);
+  metrics_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->d_metric, out, B, H, W, ergas_scale);
+  CUDA_TRY(c, cudaGetLastError());
+  c->launches += 2;
   return FDSR_OK;
 }
 

@@ -365,6 +365,100 @@ __global__ void sse_u8_kernel(const float* __restrict__ a, const float* __restri
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sse[img], double(acc));
 }
 
+// ------------------------------------------------------------------------------------------
+// Evaluation metrics of sr_mfe.py:315-345 on tensor2img-quantised uint8 images, per image:
+//   acc[b][0] = sum (a-b)^2            (compare_mse / compare_psnr / calculate_ergas)
+//   acc[b][1] = sum a                  (calculate_ergas: mean of the first image)
+//   acc[b][2] = sum of the SSIM map over the cropped interior and the 3 channels, 2^-40 fixed point
+// SSIM follows skimage.measure.compare_ssim(X, Y, multichannel=True) as the reference calls it
+// (scikit-image 0.15, _structural_similarity.py): 7x7 uniform window, K1 = 0.01, K2 = 0.03,
+// data_range = 255, sample covariance (x 49/48), float64, mean over the map cropped by 3 pixels per
+// side, then mean over channels.  Window sums are exact integers; the map is evaluated in fp64.
+// ------------------------------------------------------------------------------------------
+constexpr int kSsimWin = 7, kSsimPad = 3, kSsimTile = 16;
+constexpr double kSsimScale = 1099511627776.0;  // 2^40
+
+__global__ void __launch_bounds__(256) metrics_u8_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                         unsigned long long* __restrict__ acc, int H, int W) {
+  __shared__ uint8_t sa[kSsimTile + 6][kSsimTile + 6 + 2], sb[kSsimTile + 6][kSsimTile + 6 + 2];
+  __shared__ long long red[8][3];
+  const int img = blockIdx.z / 3, ch = blockIdx.z % 3;
+  const float* ap = a + (int64_t(img) * 3 + ch) * H * W;
+  const float* bp = b + (int64_t(img) * 3 + ch) * H * W;
+  // the block owns the 16x16 pixels at (y0, x0); its SSIM windows need a 3-pixel apron
+  const int y0 = blockIdx.y * kSsimTile, x0 = blockIdx.x * kSsimTile;
+  for (int e = threadIdx.x; e < (kSsimTile + 6) * (kSsimTile + 6); e += 256) {
+    const int ly = e / (kSsimTile + 6), lx = e - ly * (kSsimTile + 6);
+    const int y = y0 + ly - kSsimPad, x = x0 + lx - kSsimPad;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    sa[ly][lx] = in ? uint8_t(quant_u8(ap[int64_t(y) * W + x])) : 0;
+    sb[ly][lx] = in ? uint8_t(quant_u8(bp[int64_t(y) * W + x])) : 0;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kSsimTile, lx = threadIdx.x % kSsimTile;
+  const int y = y0 + ly, x = x0 + lx;
+  long long sse = 0, suma = 0, ss = 0;
+  if (y < H && x < W) {
+    const int va = sa[ly + kSsimPad][lx + kSsimPad], vb = sb[ly + kSsimPad][lx + kSsimPad];
+    sse = (long long)((va - vb) * (va - vb));
+    suma = va;
+    if (y >= kSsimPad && y < H - kSsimPad && x >= kSsimPad && x < W - kSsimPad) {
+      int s1 = 0, s2 = 0, s11 = 0, s22 = 0, s12 = 0;
+#pragma unroll
+      for (int dy = 0; dy < kSsimWin; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < kSsimWin; ++dx) {
+          const int p = sa[ly + dy][lx + dx], q = sb[ly + dy][lx + dx];
+          s1 += p;
+          s2 += q;
+          s11 += p * p;
+          s22 += q * q;
+          s12 += p * q;
+        }
+      const double np = double(kSsimWin * kSsimWin), cov = np / (np - 1.0);
+      const double ux = s1 / np, uy = s2 / np;
+      const double vx = cov * (s11 / np - ux * ux), vy = cov * (s22 / np - uy * uy), vxy = cov * (s12 / np - ux * uy);
+      const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
+      const double S = ((2.0 * ux * uy + C1) * (2.0 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+      ss = __double2ll_rn(S * kSsimScale);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    sse += __shfl_xor_sync(0xffffffffu, sse, o);
+    suma += __shfl_xor_sync(0xffffffffu, suma, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    red[warp][0] = sse;
+    red[warp][1] = suma;
+    red[warp][2] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    long long t = 0;
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+    if (t) atomicAdd(&acc[img * 4 + threadIdx.x], static_cast<unsigned long long>(t));  // integer: order-independent
+  }
+}
+
+// out[b] = (mse, psnr, ssim, ergas) in float64, exactly as sr_mfe.py derives them from the sums
+__global__ void metrics_finalize_kernel(const unsigned long long* __restrict__ acc, double* __restrict__ out, int B,
+                                        int H, int W, double scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double n = 3.0 * H * W;
+  const double sse = double(static_cast<long long>(acc[b * 4 + 0]));
+  const double mean = double(static_cast<long long>(acc[b * 4 + 1])) / n;
+  const double mse = sse / n;
+  const double nss = 3.0 * double(H - 2 * kSsimPad) * double(W - 2 * kSsimPad);
+  out[b * 4 + 0] = mse;
+  out[b * 4 + 1] = mse > 0.0 ? 10.0 * log10(255.0 * 255.0 / mse) : INFINITY;
+  out[b * 4 + 2] = (H > 2 * kSsimPad && W > 2 * kSsimPad)
+                       ? double(static_cast<long long>(acc[b * 4 + 2])) / kSsimScale / nss : NAN;
+  out[b * 4 + 3] = 100.0 * sqrt(mse / (mean * mean) / 3.0) / scale;
+}
+
 // NHWC 16-bit -> NCHW fp32 (debug hook only)
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int HW, int C) {

@@ -159,6 +159,17 @@ class Engine:
                         "fdsr_sse_u8")
         return out
 
+    def metrics_u8(self, a, b, scale: float = 4.0):
+        """Per-image (mse, psnr, ssim, ergas) of `a` (SR or bicubic image) against `b` (HR), both (B,3,H,W) fp32
+        in [-1,1]: the reference's evaluation block (sr_mfe.py:315-345) on the device.  Returns (B,4) float64."""
+        a, b = self._img(a, "a"), self._img(b, "b")
+        B, _, H, W = a.shape
+        out = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_metrics_u8(self._h, _ptr(a), _ptr(b), B, H, W, float(scale), _ptr(out),
+                                                 self._stream()), "fdsr_metrics_u8")
+        return out
+
     # ---- hooks
     def tensor_names(self):
         n = self.lib.fdsr_debug_num_tensors(self._h)

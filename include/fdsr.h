@@ -124,6 +124,14 @@ int fdsr_bicubic_u8(fdsr_ctx* ctx, const uint8_t* lr_dev, int32_t B, int32_t h, 
 int fdsr_sse_u8(fdsr_ctx* ctx, const float* a_dev, const float* b_dev, int32_t B, int32_t H,
                 int32_t W, double* sse_out_dev, void* stream);
 
+/* Device-side evaluation metrics replacing the host block of sr_mfe.py:315-356 (skimage compare_mse /
+ * compare_psnr / compare_ssim(multichannel=True) and core/metrics.py:88-93 calculate_ergas on
+ * Metrics.tensor2img uint8 images, core/metrics.py:16-42).  a = the evaluated image (SR or bicubic),
+ * b = HR, both (B,3,H,W) fp32 in [-1,1] on the device.  out_dev: B x 4 doubles (mse, psnr, ssim, ergas).
+ * SSIM: 7x7 uniform window, sample covariance, K1 = .01, K2 = .03, data_range 255, 3-pixel crop. */
+int fdsr_metrics_u8(fdsr_ctx* ctx, const float* a_dev, const float* b_dev, int32_t B, int32_t H, int32_t W,
+                    double ergas_scale, double* out_dev, void* stream);
+
 /* ---- test / profiling hooks (not part of the drop-in surface) ---- */
 /* Number of activation tensors of the current plan and their names ("downs.0", "downs.1.h", ...). */
 int32_t fdsr_debug_num_tensors(const fdsr_ctx* ctx);

@@ -437,3 +437,40 @@ def psnr_u8(a, b):
     if mse == 0:
         return float("inf")
     return 20 * math.log10(255.0 / math.sqrt(mse))
+
+
+def mse_u8(a, b):
+    """skimage.measure.compare_mse as sr_mfe.py:315 calls it (uint8 HWC images -> float64)."""
+    return float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+
+
+def ssim_u8(a, b):
+    """skimage.measure.compare_ssim(a, b, multichannel=True) as sr_mfe.py:317 calls it, restated from the
+    published algorithm of scikit-image 0.15 (`skimage/measure/_structural_similarity.py`; the package is
+    pinned in the reference's requirements.txt:6 but absent here and the reference holds no fixture with a
+    recorded SSIM value, so this restatement is PARITY UNPINNED): win_size 7 uniform filter, K1 = 0.01,
+    K2 = 0.03, data_range 255 (uint8), use_sample_covariance=True, float64; per channel the map is cropped by
+    (win_size-1)//2 on each side and averaged; channels are averaged."""
+    from scipy.ndimage import uniform_filter
+    assert a.shape == b.shape and a.ndim == 3
+    win, K1, K2, R = 7, 0.01, 0.03, 255.0
+    NP = win ** 2
+    cov_norm = NP / (NP - 1.0)
+    C1, C2 = (K1 * R) ** 2, (K2 * R) ** 2
+    pad = (win - 1) // 2
+    vals = []
+    for ch in range(a.shape[2]):
+        X = a[..., ch].astype(np.float64)
+        Y = b[..., ch].astype(np.float64)
+        ux, uy = uniform_filter(X, size=win), uniform_filter(Y, size=win)
+        uxx, uyy, uxy = uniform_filter(X * X, size=win), uniform_filter(Y * Y, size=win), uniform_filter(X * Y, size=win)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+        vals.append(S[pad:-pad, pad:-pad].mean())
+    return float(np.mean(vals))
+
+
+def ergas_u8(a, b, scale=4):
+    """core/metrics.py:88-93 calculate_ergas(img1, img2, scale)."""
+    mean2 = np.mean(a, dtype=np.float64) ** 2
+    return float(100.0 * np.sqrt(mse_u8(a, b) / mean2 / a.shape[2]) / scale)
