@@ -140,7 +140,7 @@ def run_reference(args, rank):
                                   f"batch {args.batch}/GPU (reference arm: bounded sample of 1 image per step)"},
            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -272,11 +272,26 @@ def run_ours(args, rank, world, local_rank):
                        "api": "Engine.super_resolve_u8_host -> fdsr_super_resolve_u8 (uint8 LR host -> fp32 SR host)"},
                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                "psnr_mean_vs_synthetic_hr": (acc[1] / acc[2]).item() if acc[2].item() > 0 else None}
-        print(json.dumps(out), flush=True)
+        emit(out)
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL's version banner,
+    library chatter) goes to stderr."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
     args = parse()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

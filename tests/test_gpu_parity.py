@@ -267,3 +267,46 @@ def test_full_batch_properties(ctx):
     s2 = eng.sample(c4.flip(0).contiguous(), noise=noises.flip(1).contiguous())
     assert (s1 - s2.flip(0)).abs().max().item() <= 1e-5
     del perm
+
+
+def test_infer_x4_shape_properties(ctx, oracle):
+    """BASELINE configs[3] shape (x4 128 -> 512, the UC-Merced infer config): bit-exact bicubic conditioning at
+    512^2, one UNet step against the oracle at a 128x512 strip of it (same tiles_x, ragged tile rows), and
+    size-independent properties of the full 20-step sampler at 512^2: finite, range of res2img, per-image
+    independence of batch neighbours."""
+    sd, eng = ctx["default"]
+    cfg = ctx["cfg"]
+    g = torch.Generator().manual_seed(23)
+    lr = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    up8, cond = eng.bicubic_u8(lr.cuda(), 512, 512)
+    for b in range(2):
+        assert np.array_equal(up8[b].cpu().numpy(), oracle.pil_bicubic_u8(lr[b].numpy(), 512, 512))
+    noises = torch.randn(20, 2, 3, 512, 512, generator=g).cuda()
+    both = eng.sample(cond, noise=noises)
+    assert torch.isfinite(both).all() and (both - cond).abs().max().item() <= 0.5 + 1e-6
+    one = eng.sample(cond[1:2].contiguous(), noise=noises[:, 1:2].contiguous())
+    assert (one[0] - both[1]).abs().max().item() <= 1e-5
+    # one step on a 128 x 512 strip vs the oracle (a few seconds on the host)
+    x6 = torch.cat([cond[:1, :, :128].cpu(), torch.randn(1, 3, 128, 512, generator=g)], 1)
+    t = 4
+    nl = torch.full((1, 1), float(np.float32(oracle.schedule_tables(oracle.make_beta_schedule(**oracle.DEFAULT_SCHEDULE))
+                                             ["sqrt_alphas_cumprod_prev"][t + 1])))
+    ref = oracle.unet_forward(sd, cfg, x6, nl)
+    eps = eng.unet_forward(x6[:, :3].contiguous().cuda(), x6[:, 3:].contiguous().cuda(), t).cpu()
+    r = rel_l2(eps, ref)
+    print(f"128x512 strip eps rel-L2 {r:.3e}")
+    assert r <= EPS_TOL
+
+
+def test_x8_shape_bicubic_and_step(ctx, oracle):
+    """BASELINE configs[2] shape (x8 32 -> 256): bit-exact x8 bicubic conditioning, sampler properties."""
+    _, eng = ctx["default"]
+    g = torch.Generator().manual_seed(29)
+    lr = torch.randint(0, 256, (3, 32, 32, 3), generator=g, dtype=torch.uint8)
+    up8, cond = eng.bicubic_u8(lr.cuda(), 256, 256)
+    for b in range(3):
+        assert np.array_equal(up8[b].cpu().numpy(), oracle.pil_bicubic_u8(lr[b].numpy(), 256, 256))
+    a = eng.sample(cond, seed=3)
+    again = eng.sample(cond, seed=3)
+    assert torch.equal(a, again) and torch.isfinite(a).all()
+    assert not torch.equal(a, eng.sample(cond, seed=4))
