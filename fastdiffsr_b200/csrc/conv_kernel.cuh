@@ -58,13 +58,17 @@ struct ConvCfg {
   static constexpr int kTmemCols =
       kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
   // a B stage holds as many consecutive tap blobs of one chunk as fit (N=64: 4 taps, 128: 2, 256: 1)
-  static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : (N == 64 ? 24576 : 32768);
+#ifndef FDSR_B128_BYTES
+#define FDSR_B128_BYTES 32768
+#define FDSR_B128_STAGES 2
+#endif
+  static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : (N == 64 ? 24576 : (N == 128 ? FDSR_B128_BYTES : 32768));
   // N <= 128 layers are bounded by the producer/epilogue roles, not by weight streaming: give the
   // input patch a third stage (deeper decoupling of producers and MMA) and the weights two.
   // (Measured: four patch stages with four one-tap weight stages for N = 64 removes the a_full waits
   // of the GroupNorm + 1x1-residual layers but starves the MMA warp of weights: 101 -> 132 us.)
   static constexpr int kAStages = N >= 256 ? 2 : 3;
-  static constexpr int kBStages = N >= 256 ? 3 : 2;
+  static constexpr int kBStages = N >= 256 ? 3 : (N == 128 ? FDSR_B128_STAGES : 2);
   // N = 64 layers that mix a GroupNorm 3x3 chunk with 1x1-residual chunks split the patch memory into
   // two rings (ConvLayer::nG / nR): two full stages for the 3x3 chunks and two 32 KB stages for the dense
   // centre boxes.  In a single ring of three the 3x3 chunk of the next tile could only be requested two

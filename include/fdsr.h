@@ -141,7 +141,8 @@ int fdsr_debug_read_tensor(fdsr_ctx* ctx, const char* name, float* out_dev, int6
                            int32_t* C, int32_t* H, int32_t* W, void* stream);
 /* Per-op profiling of one UNet evaluation on the context's current buffers (call after a forward
  * or sample at the shape of interest): runs the ops `reps` times with a CUDA-event pair around
- * each op's launch(es) on `stream`, writes the mean milliseconds per op to ms_out_host and returns
+ * each op's launch(es) on `stream`, writes the mean milliseconds per op to ms_out_host (for reps >= 4 the
+ * mean of the last reps/2 repetitions: the first half warms the GPU up to its sustained clocks) and returns
  * the number of ops.  Synchronous.  Op names / algorithmic conv FLOPs (at the reserved shape) for
  * turning the times into TFLOP/s: */
 int32_t fdsr_debug_num_ops(const fdsr_ctx* ctx);

@@ -25,7 +25,7 @@ cond = (torch.rand(B, 3, H, H, device="cuda") * 2 - 1)
 x = torch.randn(B, 3, H, H, device="cuda")
 eng.unet_forward(cond, x, 5)
 torch.cuda.synchronize()
-prof = eng.profile_unet(5, reps=3)
+prof = eng.profile_unet(5, reps=int(os.environ.get("FDSR_PROF_REPS", "3")))
 tot_ms = sum(p[1] for p in prof)
 tot_fl = sum(p[2] for p in prof)
 print(f"B={B} {H}x{H} {dtype}: workspace {eng.workspace_bytes() / 2**30:.2f} GiB, unet flops {eng.unet_flops() / 1e9:.1f} G")
