@@ -129,7 +129,7 @@ struct fdsr_ctx {
   bool tma_in = true;    // FDSR_TMA_IN=0: producer warps gather every input patch (no TMA loads of the A operand)
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
-  bool cluster2 = false; // FDSR_CLUSTER=1: 2-CTA clusters with multicast weight stages (measured: no gain yet)
+  bool cluster2 = false; // FDSR_CLUSTER=1: 2-CTA clusters with multicast weight stages (measured twice: no gain)
   cudaGraphExec_t graph = nullptr;
   struct {
     int B = 0, H = 0, W = 0;

@@ -305,7 +305,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   // Split-N (L.nsplit > 1, low-resolution layers whose tile count would leave most SMs idle): CTA
   // `part` computes output channels [part*N, part*N + N) of the n_full-wide layer for its tiles.
   const int nsplit = L.nsplit;
-  const int part = int(blockIdx.x) % nsplit;
+  const int part = int(blockIdx.x) % nsplit;  // (split-N layers are never clustered)
   const int n_off = part * N, n_full = L.n_full;
   const int nclusters = int(gridDim.x / csize) / nsplit, cid = int(blockIdx.x / csize) / nsplit;
   const int nunits = ngroups / int(csize);
@@ -434,7 +434,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // GroupNorm chunks land on raw_full (the producer warps transform them in place and then arrive on
     // a_full); raw chunks complete a_full directly, so the MMA warp starts as soon as the bytes are there.
     const bool tma_in = L.a_tma != 0;
-    if (tma_in) asm volatile("griddepcontrol.wait;" ::: "memory");  // patches are the previous layer's output
+    // Patches are the previous layer's output: no patch request before griddepcontrol.wait.  Weights are
+    // constants, so the first weight stages are requested before it and land while the previous launch drains.
+    bool dep_ok = !tma_in;
     const int total = (tile_end - tile_begin) * L.nchunks;
     // patch cursor
     int a_next = tma_in ? 0 : total, a_c = 0, a_gs = 0, a_gph = 0, a_rs = 0, a_rph = 0;
@@ -452,9 +454,14 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const int total_taps = (tile_end - tile_begin) * taps_tile;
     int b_q = 0, b_qq = 0, bs = 0, bph = 0;  // next tap overall / inside its tile
     const uint8_t* const w0 = L.weights + size_t(n_off) * 16;
+    int b_issued = 0;
     while (a_next < total || b_q < total_taps) {
       bool progress = false;
-      if (a_next < total) {
+      if (!dep_ok && (b_issued >= Cfg::kBStages || b_q >= total_taps)) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        dep_ok = true;
+      }
+      if (dep_ok && a_next < total) {
         const bool a_r1 = L.chunk[a_c].ring != 0;
         const int a_as = a_r1 ? nG + a_rs : a_gs;
         const uint32_t ok = mbar_test(bar_a_empty(a_as), (a_r1 ? a_rph : a_gph) ^ 1) ? 1u : 0u;
@@ -526,6 +533,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
           b_q += g;
           b_qq = (b_qq + g) % taps_tile;
+          ++b_issued;
           progress = true;
         }
       }
