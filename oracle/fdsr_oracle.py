@@ -121,13 +121,18 @@ def state_dict_spec(cfg):
     return [("denoise_fn." + k, s, kind, f) for (k, s, kind, f) in out]
 
 
-def make_state_dict(cfg, seed=0, gn_jitter=0.0):
+def make_state_dict(cfg, seed=0, gn_jitter=0.0, spec=None):
     """Deterministic, machine-independent random weights with PyTorch's default-init statistics
     (conv/linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in)); GroupNorm: gamma=1, beta=0, optionally
-    jittered so that the affine path is exercised).  numpy PCG64, one stream per tensor."""
+    jittered so that the affine path is exercised).  numpy PCG64, one stream per tensor.
+    ``spec`` defaults to the FastDiffSR UNet's; pass ``sr3_state_dict_spec(...)`` for the SR3 baseline."""
     sd = {}
-    for idx, (key, shape, kind, fan_in) in enumerate(state_dict_spec(cfg)):
+    for idx, (key, shape, kind, fan_in) in enumerate(spec if spec is not None else state_dict_spec(cfg)):
         rng = np.random.default_rng([seed, idx])
+        if kind == "inv_freq":  # TimeEmbedding buffer (ddpm_modules/unet.py:22-27), not random
+            dim = 2 * shape[0]
+            sd[key] = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32) * (-math.log(10000) / dim))
+            continue
         if kind in ("w", "b"):
             bound = 1.0 / math.sqrt(fan_in)
             a = rng.uniform(-bound, bound, size=shape)
@@ -474,3 +479,206 @@ def ergas_u8(a, b, scale=4):
     """core/metrics.py:88-93 calculate_ergas(img1, img2, scale)."""
     mean2 = np.mean(a, dtype=np.float64) ** 2
     return float(100.0 * np.sqrt(mse_u8(a, b) / mean2 / a.shape[2]) / scale)
+
+
+# --------------------------------------------------------------------------------------
+# SR3 baseline (which_model_G == "ddpm"): the comparison model of the paper, SURVEY section 8(f) N3.
+# Restates model/ddpm_modules/unet.py (TimeEmbedding :19-33, ResnetBlock :79-97, SelfAttention
+# :100-131, ResnetBlocWithAttn :134-147, UNet :150-243) and the sampler of
+# model/ddpm_modules/diffusion.py (:159-199 posterior / p_sample, :201-231 p_sample_loop).
+# Pinned against the real reference by oracle/make_golden.py (tests/golden/sr3_*.npz).
+# --------------------------------------------------------------------------------------
+
+SR3_UNET = dict(in_channel=6, out_channel=3, inner_channel=64, norm_groups=32,
+                channel_multiplier=[1, 1, 2, 2, 4, 4], attn_res=[16], res_blocks=2, dropout=0.2)
+SR3_SCHEDULE = dict(schedule="linear", n_timestep=1000, linear_start=1e-4, linear_end=2e-2)
+
+
+def sr3_unet_layers(cfg, image_size=256):
+    """Structural plan of the SR3 UNet (ddpm_modules/unet.py:178-225): like ``unet_layers`` but a
+    block carries SelfAttention when the resolution *of the configured image_size* at its level is in
+    attn_res (the flag does not depend on the actual input size), and mid[0] always does."""
+    inner = cfg["inner_channel"]
+    mults = list(cfg["channel_multiplier"])
+    nres = cfg["res_blocks"]
+    attn_res = list(cfg["attn_res"])
+    pre = inner
+    feat = [pre]
+    now = image_size
+    downs = [("stem", "downs.0", cfg["in_channel"], inner)]
+    for li, m in enumerate(mults):
+        cm = inner * m
+        for _ in range(nres):
+            downs.append(("res", f"downs.{len(downs)}", pre, cm, now in attn_res))
+            feat.append(cm)
+            pre = cm
+        if li != len(mults) - 1:
+            downs.append(("down", f"downs.{len(downs)}", pre))
+            feat.append(pre)
+            now //= 2
+    mid = [("res", "mid.0", pre, pre, True), ("res", "mid.1", pre, pre, False)]
+    ups = []
+    for li in reversed(range(len(mults))):
+        cm = inner * mults[li]
+        for _ in range(nres + 1):
+            ups.append(("res", f"ups.{len(ups)}", pre + feat.pop(), cm, now in attn_res))
+            pre = cm
+        if li >= 1:
+            ups.append(("up", f"ups.{len(ups)}", pre))
+            now *= 2
+    return downs, mid, ups, pre
+
+
+def sr3_state_dict_spec(cfg, image_size=256):
+    """[(key, shape, kind, fan_in)] in the reference's state_dict order for the SR3 UNet."""
+    inner = cfg["inner_channel"]
+    out = [("time_mlp.0.inv_freq", (inner // 2,), "inv_freq", 0)]
+
+    def conv(name, co, ci, k, bias=True):
+        out.append((name + ".weight", (co, ci, k, k), "w", ci * k * k))
+        if bias:
+            out.append((name + ".bias", (co,), "b", ci * k * k))
+
+    def lin(name, co, ci):
+        out.append((name + ".weight", (co, ci), "w", ci))
+        out.append((name + ".bias", (co,), "b", ci))
+
+    def gn(name, c):
+        out.append((name + ".weight", (c,), "gamma", 0))
+        out.append((name + ".bias", (c,), "beta", 0))
+
+    def res(name, ci, co, attn):
+        lin(f"{name}.res_block.mlp.1", co, inner)
+        gn(f"{name}.res_block.block1.block.0", ci)
+        conv(f"{name}.res_block.block1.block.3", co, ci, 3)
+        gn(f"{name}.res_block.block2.block.0", co)
+        conv(f"{name}.res_block.block2.block.3", co, co, 3)
+        if ci != co:
+            conv(f"{name}.res_block.res_conv", co, ci, 1)
+        if attn:
+            gn(f"{name}.attn.norm", co)
+            conv(f"{name}.attn.qkv", 3 * co, co, 1, bias=False)
+            conv(f"{name}.attn.out", co, co, 1)
+
+    lin("time_mlp.1", inner * 4, inner)
+    lin("time_mlp.3", inner, inner * 4)
+    downs, mid, ups, last = sr3_unet_layers(cfg, image_size)
+    for grp in (downs, mid, ups):
+        for e in grp:
+            if e[0] == "stem":
+                conv(e[1], e[3], e[2], 3)
+            elif e[0] == "res":
+                res(e[1], e[2], e[3], e[4])
+            else:
+                conv(e[1] + ".conv", e[2], e[2], 3)
+    gn("final_conv.block.0", last)
+    conv("final_conv.block.3", cfg["out_channel"], last, 3)
+    return [("denoise_fn." + k, s, kind, f) for (k, s, kind, f) in out]
+
+
+def sr3_time_embedding(sd, cfg, time):
+    """time_mlp (ddpm_modules/unet.py:165-171): time (B,) -> (B, inner)."""
+    inv = sd["denoise_fn.time_mlp.0.inv_freq"]
+    sinus = torch.ger(time.view(-1).float(), inv)
+    t = torch.cat([sinus.sin(), sinus.cos()], dim=-1)
+    t = F.linear(t, sd["denoise_fn.time_mlp.1.weight"], sd["denoise_fn.time_mlp.1.bias"])
+    return F.linear(_swish(t), sd["denoise_fn.time_mlp.3.weight"], sd["denoise_fn.time_mlp.3.bias"])
+
+
+def sr3_self_attention(sd, pfx, x, groups, taps=None, name=None):
+    """SelfAttention.forward, n_head = 1 (ddpm_modules/unet.py:110-131): note the 1/sqrt(channel) scale."""
+    B, C, H, W = x.shape
+    n = F.group_norm(x, groups, sd[pfx + ".norm.weight"], sd[pfx + ".norm.bias"], eps=1e-5)
+    qkv = F.conv2d(n, sd[pfx + ".qkv.weight"]).view(B, 1, 3 * C, H, W)
+    q, k, v = qkv.chunk(3, dim=2)
+    attn = torch.einsum("bnchw, bncyx -> bnhwyx", q, k).contiguous() / math.sqrt(C)
+    attn = torch.softmax(attn.view(B, 1, H, W, -1), -1).view(B, 1, H, W, H, W)
+    o = torch.einsum("bnhwyx, bncyx -> bnchw", attn, v).contiguous().view(B, C, H, W)
+    if taps is not None:
+        taps[name + ".attn.q"] = q.reshape(B, C, H, W)
+        taps[name + ".attn.k"] = k.reshape(B, C, H, W)
+        taps[name + ".attn.v"] = v.reshape(B, C, H, W)
+        taps[name + ".attn.o"] = o
+    return F.conv2d(o, sd[pfx + ".out.weight"], sd[pfx + ".out.bias"]) + x
+
+
+def _sr3_res_block(sd, name, x, temb, groups, with_attn, taps=None):
+    p = f"denoise_fn.{name}.res_block"
+    h = _gn_swish_conv(sd, p + ".block1", x, groups)
+    h = h + F.linear(_swish(temb), sd[p + ".mlp.1.weight"], sd[p + ".mlp.1.bias"])[:, :, None, None]
+    h = _gn_swish_conv(sd, p + ".block2", h, groups)
+    if p + ".res_conv.weight" in sd:
+        x = F.conv2d(x, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
+    y = h + x
+    if with_attn:
+        if taps is not None:
+            taps[name + ".res"] = y
+        y = sr3_self_attention(sd, f"denoise_fn.{name}.attn", y, groups, taps, name)
+    return y
+
+
+@torch.no_grad()
+def sr3_unet_forward(sd, cfg, x, time, image_size=256, taps=None):
+    """eps = UNet(cat[cond, x_t], t) of the SR3 baseline.  x: (B,6,H,W) fp32, time: (B,) integer steps."""
+    groups = cfg.get("norm_groups") or 32
+    downs, mid, ups, _ = sr3_unet_layers(cfg, image_size)
+    t = sr3_time_embedding(sd, cfg, time)
+    feats = []
+    for e in downs:
+        if e[0] == "stem":
+            x = F.conv2d(x, sd[f"denoise_fn.{e[1]}.weight"], sd[f"denoise_fn.{e[1]}.bias"], padding=1)
+        elif e[0] == "res":
+            x = _sr3_res_block(sd, e[1], x, t, groups, e[4], taps)
+        else:
+            x = F.conv2d(x, sd[f"denoise_fn.{e[1]}.conv.weight"], sd[f"denoise_fn.{e[1]}.conv.bias"],
+                         stride=2, padding=1)
+        feats.append(x)
+        if taps is not None:
+            taps[e[1]] = x
+    for e in mid:
+        x = _sr3_res_block(sd, e[1], x, t, groups, e[4], taps)
+        if taps is not None:
+            taps[e[1]] = x
+    for e in ups:
+        if e[0] == "res":
+            x = _sr3_res_block(sd, e[1], torch.cat((x, feats.pop()), dim=1), t, groups, e[4], taps)
+        else:
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+            x = F.conv2d(x, sd[f"denoise_fn.{e[1]}.conv.weight"], sd[f"denoise_fn.{e[1]}.conv.bias"], padding=1)
+        if taps is not None:
+            taps[e[1]] = x
+    h = F.group_norm(x, groups, sd["denoise_fn.final_conv.block.0.weight"],
+                     sd["denoise_fn.final_conv.block.0.bias"], eps=1e-5)
+    return F.conv2d(_swish(h), sd["denoise_fn.final_conv.block.3.weight"],
+                    sd["denoise_fn.final_conv.block.3.bias"], padding=1)
+
+
+@torch.no_grad()
+def sr3_sample_loop(sd, cfg, tables, cond, noises, image_size=256, continous=False, trace=None):
+    """p_sample_loop of the SR3 baseline (ddpm_modules/diffusion.py:201-231) with injected noise.
+
+    noises: (T,B,3,H,W) in the draw order x_T, then z for t = T-1 .. 1.  (The reference also draws a
+    tensor at t = 0 and multiplies it by the zero mask, :196-199; it does not enter the result.)
+    The image itself is predicted (no res2img).  Returns (B,3,H,W); the reference returns
+    ``ret_img[-1]`` = the last image without the batch axis (identical for B = 1 up to that axis).
+    continous=True: [cond, frames at t % (1 | T//10) == 0] stacked per sample along dim 0."""
+    T = len(tables["betas"])
+    sample_inter = 1 | (T // 10)
+    x = noises[0]
+    B = cond.shape[0]
+    frames = []
+    for k, t in enumerate(reversed(range(T))):
+        x_in = x
+        eps = sr3_unet_forward(sd, cfg, torch.cat([cond, x], dim=1), torch.full((B,), t, dtype=torch.long), image_size)
+        x0 = _f32(tables, "sqrt_recip_alphas_cumprod", t) * x - _f32(tables, "sqrt_recipm1_alphas_cumprod", t) * eps
+        x0 = x0.clamp(-1.0, 1.0)
+        mean = _f32(tables, "posterior_mean_coef1", t) * x0 + _f32(tables, "posterior_mean_coef2", t) * x
+        sigma = (0.5 * _f32(tables, "posterior_log_variance_clipped", t)).exp()
+        x = mean + (sigma * noises[k + 1] if t > 0 else 0.0)
+        if trace is not None:
+            trace.append(dict(t=t, x_t=x_in, eps=eps, x_prev=x))
+        if t % sample_inter == 0:
+            frames.append(x)
+    if not continous:
+        return x
+    return torch.cat([torch.cat([cond[b:b + 1]] + [f[b:b + 1] for f in frames], dim=0) for b in range(B)], dim=0)

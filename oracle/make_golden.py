@@ -78,6 +78,100 @@ def run_ref_sampler(netG, cond, noises, continous):
     return out
 
 
+def run_ref_sampler_sr3(netG, cond, noises, continous):
+    """The SR3 baseline's sampler (ddpm_modules/diffusion.py:201-231) draws torch.randn for x_T and then,
+    through noise_like (:70-76), one torch.randn per step including t = 0 (where it is masked out)."""
+    import model.ddpm_modules.diffusion as D
+    queue = [noises[i] for i in range(noises.shape[0])] + [torch.zeros_like(noises[0])]
+
+    class _T:
+        def __getattr__(self, k):
+            return getattr(torch, k)
+
+        @staticmethod
+        def randn(shape, device=None):
+            return queue.pop(0).clone()
+
+    real = D.torch
+    D.torch = _T()
+    try:
+        out = netG.super_resolution(cond, continous)
+    finally:
+        D.torch = real
+    assert len(queue) == 0, "reference consumed %d fewer noise tensors than provided" % len(queue)
+    return out
+
+
+def sr3_noise(T, B, H, seed):
+    """Injected noise of the SR3 fixtures: regenerated from the seed by the tests (kept out of the fixtures
+    for size); the fixture stores a checksum."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(T, B, 3, H, H, generator=g)
+
+
+def main_sr3():
+    """SR3 baseline (which_model_G = 'ddpm', config/sr_ddpm_test_64_256.json): state_dict surface, UNet forward
+    (two configurations: the shipped one — attention at 16x16 of a 256 image — and image_size 64 so that the
+    fixture's 64x64 input runs attention on 16x16 = 256 tokens with 128 channels), and the sampler with a
+    short T = 12 linear schedule, all against the real reference."""
+    import model.networks as networks
+    ok = True
+    opt = load_ref_cfg("sr_ddpm_test_64_256.json")
+    ucfg = dict(opt["model"]["unet"])
+    ucfg["norm_groups"] = 32
+    for k in O.SR3_UNET:
+        assert O.SR3_UNET[k] == ucfg[k], k
+    assert opt["model"]["beta_schedule"]["val"] == O.SR3_SCHEDULE, opt["model"]["beta_schedule"]["val"]
+    for image_size in (256, 64):
+        opt["model"]["diffusion"]["image_size"] = image_size
+        torch.manual_seed(0)
+        netG0 = networks.define_G(opt)
+        ref_keys = [(k, tuple(v.shape)) for k, v in netG0.state_dict().items()]
+        my_keys = [(k, s) for (k, s, _, _) in O.sr3_state_dict_spec(ucfg, image_size)]
+        assert ref_keys == my_keys, "sr3 state_dict spec mismatch"
+        print(f"sr3[image_size={image_size}] state_dict spec: {len(my_keys)} tensors identical")
+        sd = O.make_state_dict(ucfg, seed=3, gn_jitter=0.2, spec=O.sr3_state_dict_spec(ucfg, image_size))
+        assert torch.equal(sd["denoise_fn.time_mlp.0.inv_freq"], netG0.state_dict()["denoise_fn.time_mlp.0.inv_freq"])
+        sched = dict(schedule="linear", n_timestep=12, linear_start=1e-4, linear_end=0.35)
+        netG = networks.define_G(opt)
+        netG.set_new_noise_schedule(sched, "cpu")
+        netG.load_state_dict(sd, strict=False)
+        netG.eval()
+        tab = O.schedule_tables(O.make_beta_schedule(**sched))
+        H = 128 if image_size == 256 else 64
+        g = torch.Generator().manual_seed(21)
+        x6 = torch.randn(2, 6, H, H, generator=g).half().float()   # stored as fp16 (exactly representable)
+        steps = [11, 640]   # time is embedded as a float: any integer step of a T=1000 schedule is a valid input
+        eps_ref = []
+        for t in steps:
+            tt = torch.full((2,), t, dtype=torch.long)
+            with torch.no_grad():
+                r = netG.denoise_fn(x6, tt)
+            m = O.sr3_unet_forward(sd, ucfg, x6, tt, image_size)
+            d = (r - m).abs().max().item()
+            print(f"sr3 unet[image_size={image_size}] t={t}: max|ref-oracle| = {d:.3e}, |ref| max {r.abs().max():.3f}")
+            ok &= d <= 1e-5
+            eps_ref.append(r.numpy())
+        cond = torch.rand(1, 3, H, H, generator=g) * 2 - 1
+        noises = sr3_noise(12, 1, H, 22)
+        sr_ref = run_ref_sampler_sr3(netG, cond, noises, False)
+        sr_ref_c = run_ref_sampler_sr3(netG, cond, noises, True)
+        sr_m = O.sr3_sample_loop(sd, ucfg, tab, cond, noises, image_size, False)
+        sr_m_c = O.sr3_sample_loop(sd, ucfg, tab, cond, noises, image_size, True)
+        d1 = (sr_ref - sr_m[0]).abs().max().item()
+        d2 = (sr_ref_c - sr_m_c).abs().max().item()
+        print(f"sr3 sampler[image_size={image_size}] T=12 {H}x{H}: max|ref-oracle| = {d1:.3e} "
+              f"(continous: {d2:.3e}, shape {tuple(sr_ref_c.shape)}; plain returns {tuple(sr_ref.shape)})")
+        ok &= d1 <= 1e-4 and d2 <= 1e-4 and sr_ref_c.shape == sr_m_c.shape
+        np.savez_compressed(os.path.join(GOLD, f"sr3_{image_size}.npz"), x6=x6.numpy().astype(np.float16),
+                            steps=np.array(steps), eps=np.stack(eps_ref), cond=cond.numpy(),
+                            noise_seed=22, noise_sum=float(noises.double().sum()), sr=sr_ref.numpy(),
+                            sr_continous=sr_ref_c[::4].numpy(), image_size=image_size,   # frames 0, 4, 8, 12
+                           
+                            sched=json.dumps(sched), gn_jitter=0.2, seed=3)
+    return ok
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -178,6 +272,7 @@ def main():
         keep[f"syn_sr_{h}"] = pil
     np.savez_compressed(os.path.join(GOLD, "bicubic.npz"), **keep)
 
+    ok &= main_sr3()
     print("GOLDEN", "OK" if ok else "MISMATCH")
     sys.exit(0 if ok else 1)
 
