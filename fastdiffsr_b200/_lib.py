@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("FDSR_LIB", os.path.join(_HERE, "libfdsr.so"))
 CSRC = os.path.join(_HERE, "csrc")
 MAX_LEVELS = 8
 DTYPE_FP16, DTYPE_BF16, DTYPE_FP32 = 0, 1, 2
+MODEL_FASTDIFFSR, MODEL_SR3 = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -22,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 class FdsrConfig(C.Structure):
     _fields_ = [("in_channel", C.c_int32), ("out_channel", C.c_int32), ("inner_channel", C.c_int32),
                 ("norm_groups", C.c_int32), ("n_levels", C.c_int32), ("channel_mults", C.c_int32 * MAX_LEVELS),
-                ("res_blocks", C.c_int32), ("dtype", C.c_int32)]
+                ("res_blocks", C.c_int32), ("dtype", C.c_int32), ("model", C.c_int32), ("attn_levels", C.c_int32)]
 
 
 class FdsrError(RuntimeError):

@@ -16,6 +16,7 @@
 #include "aux_kernels.cuh"
 #include "conv_kernel.cuh"
 #include "conv_f32.cuh"
+#include "attn_kernel.cuh"
 
 using namespace fdsr;
 
@@ -40,6 +41,7 @@ struct HChunk {
   std::string wname;
   int wc0;      // first input channel inside the weight tensor
   int creal;    // real (non-padded) channels in this chunk
+  int kk = 3;   // kernel size of the weight tensor (3, or 1 for res_conv / attention projections)
 };
 struct HConv {
   std::string name;
@@ -51,6 +53,8 @@ struct HConv {
   std::vector<std::string> bias_names;
   std::string film_name;
   int resid = -1, out = -1, out_mode = kOutAct, out_c = 0;
+  int w_n0 = 0, w_rows = 0;  // this launch uses rows [w_n0, w_n0 + cout) of a weight tensor with w_rows rows (0 = cout)
+  bool film_swish = false;   // FiLM vector = Linear(swish(emb)) (SR3 ResnetBlock.mlp) instead of Linear(emb)
   // device-side resources
   size_t w_off = 0;      // into weight arena
   size_t gamma_off = 0;  // into param arena (floats)
@@ -58,11 +62,13 @@ struct HConv {
 };
 struct HAttn {
   std::string name;
+  int kind = 0;  // 0: CLAM + SLAM gates (FastDiffSR mid[0]); 1: SelfAttention core softmax(q k^T / sqrt(C)) v (SR3)
   int in = -1, out = -1, C = 0;
+  int tq = -1, tk = -1, tv = -1;              // kind 1: q / k / v tensors (`out` is the un-projected attention output)
   size_t w1_off = 0, w2_off = 0, w7_off = 0;  // param arena (floats)
 };
 struct HOp {
-  int kind;  // 0 conv, 1 attention gates
+  int kind;  // 0 conv, 1 attention (HAttn)
   int idx;
 };
 
@@ -100,6 +106,8 @@ struct fdsr_ctx {
   std::vector<ConvLayer> h_layers;  // passed by value as __grid_constant__ kernel parameters
   std::vector<F32Layer> f_layers;   // fp32 parity mode: the same plan for conv_f32_kernel
   std::vector<F32GnArgs> f_gn;
+  std::vector<AttnParams> a_params;  // per HAttn of kind 1 (16-bit modes)
+  bool attn_ref = false;             // FDSR_ATTN_REF=1: CUDA-core attention core in the 16-bit modes too
   float* d_weights32 = nullptr;     // fp32 parity mode weights: per conv, per chunk [tap][ci][N]
   std::vector<size_t> w32_off;      // per conv (floats)
   size_t off_gntab = 0;             // [B][kMaxGnC] float2 scratch of the fp32 mode
@@ -203,7 +211,9 @@ int add_res(fdsr_ctx* c, const std::string& name, const std::vector<int>& srcs, 
       for (int c0 = 0; c0 < c->tensors[srcs[si]].C; c0 += 64, vc += 64)
         k.chunks.push_back({int(si), c0, 1, vc, -1, taps3x3(), p + ".block1.block.3.weight", vc, 64});
     k.bias_names = {p + ".block1.block.3.bias"};
-    k.film_name = p + ".noise_func.noise_func.0";
+    // FeatureWiseAffine (fastdiffsr unet.py:38-54): Linear(emb); SR3 ResnetBlock.mlp (ddpm unet.py:82-85): Linear(swish(emb))
+    k.film_swish = c->cfg.model == FDSR_MODEL_SR3;
+    k.film_name = k.film_swish ? p + ".mlp.1" : p + ".noise_func.noise_func.0";
     k.out = th;
     c->convs.push_back(k);
     c->ops.push_back({0, int(c->convs.size()) - 1});
@@ -226,7 +236,7 @@ int add_res(fdsr_ctx* c, const std::string& name, const std::vector<int>& srcs, 
       for (size_t si = 0; si < srcs.size(); ++si) {
         k.src[k.nsrc] = srcs[si];
         for (int c0 = 0; c0 < c->tensors[srcs[si]].C; c0 += 64, vc += 64)
-          k.chunks.push_back({k.nsrc, c0, 0, 0, -1, {{0, 0, kPatchW + 1}}, p + ".res_conv.weight", vc, 64});
+          k.chunks.push_back({k.nsrc, c0, 0, 0, -1, {{0, 0, kPatchW + 1}}, p + ".res_conv.weight", vc, 64, 1});
         ++k.nsrc;
       }
       k.bias_names.push_back(p + ".res_conv.bias");
@@ -240,6 +250,72 @@ int add_res(fdsr_ctx* c, const std::string& name, const std::vector<int>& srcs, 
   return to;
 }
 
+// SelfAttention of the SR3 baseline (ddpm_modules/unet.py:100-131) on tensor `in` (C channels):
+//   q, k, v = three 1x1 convs with GroupNorm (no activation) fused into their prologue, weights = row blocks of
+//             attn.qkv.weight (n_head = 1: chunk(3) along the channel axis);
+//   o       = softmax(q k^T / sqrt(C)) v  (attn_kernel.cuh);
+//   out     = 1x1 conv(o) + bias + in, with the GroupNorm statistics of the result.
+int add_self_attn(fdsr_ctx* c, const std::string& name, int in, int level, const std::string& out_name) {
+  const std::string p = "denoise_fn." + name + ".attn";
+  const int C = c->tensors[in].C;
+  int tq[3];
+  const char* sfx[3] = {".attn.q", ".attn.k", ".attn.v"};
+  for (int i = 0; i < 3; ++i) {
+    tq[i] = add_tensor(c, name + sfx[i], C, level, false);
+    HConv k;
+    k.name = name + sfx[i];
+    k.N = pad_n(C);
+    k.cout = C;
+    k.nsrc = 1;
+    k.src[0] = in;
+    k.gn_C = C;
+    k.gn_nsrc = 1;
+    k.gn_name = p + ".norm";
+    for (int c0 = 0; c0 < C; c0 += 64)
+      k.chunks.push_back({0, c0, 2, c0, -1, {{0, 0, kPatchW + 1}}, p + ".qkv.weight", c0, 64, 1});
+    k.w_n0 = i * C;
+    k.w_rows = 3 * C;
+    k.out = tq[i];
+    c->convs.push_back(k);
+    c->ops.push_back({0, int(c->convs.size()) - 1});
+  }
+  HAttn a;
+  a.name = name;
+  a.kind = 1;
+  a.in = in;
+  a.C = C;
+  a.tq = tq[0];
+  a.tk = tq[1];
+  a.tv = tq[2];
+  a.out = add_tensor(c, name + ".attn.o", C, level, false);
+  c->attns.push_back(a);
+  c->ops.push_back({1, int(c->attns.size()) - 1});
+  const int to = add_tensor(c, out_name, C, level, true);
+  {
+    HConv k;
+    k.name = name + ".attn.out";
+    k.N = pad_n(C);
+    k.cout = C;
+    k.nsrc = 1;
+    k.src[0] = a.out;
+    for (int c0 = 0; c0 < C; c0 += 64)
+      k.chunks.push_back({0, c0, 0, 0, -1, {{0, 0, kPatchW + 1}}, p + ".out.weight", c0, 64, 1});
+    k.bias_names = {p + ".out.bias"};
+    k.resid = in;
+    k.out = to;
+    c->convs.push_back(k);
+    c->ops.push_back({0, int(c->convs.size()) - 1});
+  }
+  return to;
+}
+
+// ResnetBlocWithAttn (ddpm_modules/unet.py:134-147): ResnetBlock, then SelfAttention when `attn`
+int add_res_attn(fdsr_ctx* c, const std::string& name, const std::vector<int>& srcs, int cout, int level, bool attn) {
+  if (!attn) return add_res(c, name, srcs, cout, level, name);
+  const int tr = add_res(c, name, srcs, cout, level, name + ".res");
+  return add_self_attn(c, name, tr, level, name);
+}
+
 int build_plan(fdsr_ctx* c) {
   const fdsr_config& g = c->cfg;
   const int inner = g.inner_channel;
@@ -248,6 +324,8 @@ int build_plan(fdsr_ctx* c) {
   if (inner % 64 != 0) return fail(c, FDSR_E_INVALID, "inner_channel must be a multiple of 64");
   if (g.norm_groups != 32) return fail(c, FDSR_E_INVALID, "norm_groups must be 32");
   if (g.n_levels < 1 || g.n_levels > FDSR_MAX_LEVELS) return fail(c, FDSR_E_INVALID, "bad n_levels");
+  if (g.model != FDSR_MODEL_FASTDIFFSR && g.model != FDSR_MODEL_SR3) return fail(c, FDSR_E_INVALID, "unknown model %d", g.model);
+  const bool sr3 = g.model == FDSR_MODEL_SR3;
   for (int i = 0; i < g.n_levels; ++i)
     if (g.channel_mults[i] < 1 || inner * g.channel_mults[i] > 256)
       return fail(c, FDSR_E_INVALID, "channel width %d unsupported (max 256 output channels)",
@@ -274,7 +352,7 @@ int build_plan(fdsr_ctx* c) {
     const int cm = inner * g.channel_mults[li];
     for (int r = 0; r < g.res_blocks; ++r, ++idx) {
       const std::string nm = "downs." + std::to_string(idx);
-      cur = add_res(c, nm, {cur}, cm, level, nm);
+      cur = add_res_attn(c, nm, {cur}, cm, level, sr3 && ((g.attn_levels >> li) & 1));
       feats.push_back(cur);
       pre = cm;
     }
@@ -306,8 +384,11 @@ int build_plan(fdsr_ctx* c) {
       feats.push_back(cur);
     }
   }
-  // mid: ResnetBlock + CLAM/SLAM, ResnetBlock (unet.py:274-279)
-  {
+  // mid: ResnetBlock + CLAM/SLAM, ResnetBlock (unet.py:274-279); SR3: ResnetBlock + SelfAttention, ResnetBlock
+  if (sr3) {
+    cur = add_res_attn(c, "mid.0", {cur}, pre, level, true);
+    cur = add_res_attn(c, "mid.1", {cur}, pre, level, false);
+  } else {
     const int tr = add_res(c, "mid.0", {cur}, pre, level, "mid.0.res");
     HAttn a;
     a.name = "mid.0";
@@ -325,7 +406,7 @@ int build_plan(fdsr_ctx* c) {
       const int skip = feats.back();
       feats.pop_back();
       const std::string nm = "ups." + std::to_string(idx);
-      cur = add_res(c, nm, {cur, skip}, cm, level, nm);
+      cur = add_res_attn(c, nm, {cur, skip}, cm, level, sr3 && ((g.attn_levels >> li) & 1));
       pre = cm;
     }
     if (li >= 1) {
@@ -421,9 +502,9 @@ int pack_weights(fdsr_ctx* c) {
     for (const HChunk& ch : k.chunks) {
       const std::vector<float>* w = find_w(c, ch.wname);
       if (!w) return fail(c, FDSR_E_NOTFOUND, "missing weight %s", ch.wname.c_str());
-      const bool is1x1 = ch.wname.find("res_conv") != std::string::npos;
-      const int kk = is1x1 ? 1 : 3;
-      const size_t cin_w = w->size() / (size_t(k.cout) * kk * kk);
+      const bool is1x1 = ch.kk == 1;
+      const int kk = ch.kk;
+      const size_t cin_w = w->size() / (size_t(k.w_rows ? k.w_rows : k.cout) * kk * kk);
       for (const HTap& tp : ch.taps) {
         T* blob = host.data() + off / sizeof(T);
         for (int cg = 0; cg < k.ncg; ++cg)
@@ -431,7 +512,7 @@ int pack_weights(fdsr_ctx* c) {
             for (int j = 0; j < 8; ++j) {
               const int ci = cg * 8 + j;
               if (ci >= ch.creal) continue;
-              const size_t wi = ((size_t(n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk +
+              const size_t wi = ((size_t(k.w_n0 + n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk +
                                 (is1x1 ? 0 : tp.kx);
               blob[(size_t(cg) * k.N + n) * 8 + j] = to_t<T>((*w)[wi]);
             }
@@ -462,14 +543,14 @@ int pack_weights_f32(fdsr_ctx* c) {
     for (const HChunk& ch : k.chunks) {
       const std::vector<float>* w = find_w(c, ch.wname);
       if (!w) return fail(c, FDSR_E_NOTFOUND, "missing weight %s", ch.wname.c_str());
-      const bool is1x1 = ch.wname.find("res_conv") != std::string::npos;
-      const int kk = is1x1 ? 1 : 3;
-      const size_t cin_w = w->size() / (size_t(k.cout) * kk * kk);
+      const bool is1x1 = ch.kk == 1;
+      const int kk = ch.kk;
+      const size_t cin_w = w->size() / (size_t(k.w_rows ? k.w_rows : k.cout) * kk * kk);
       for (const HTap& tp : ch.taps) {
         for (int ci = 0; ci < ch.creal; ++ci)
           for (int n = 0; n < k.cout; ++n)
             host[off + size_t(ci) * k.N + n] =
-                (*w)[((size_t(n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk + (is1x1 ? 0 : tp.kx)];
+                (*w)[((size_t(k.w_n0 + n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk + (is1x1 ? 0 : tp.kx)];
         off += size_t(ch.creal) * k.N;
       }
     }
@@ -494,6 +575,7 @@ int upload_params(fdsr_ctx* c) {
     p.insert(p.end(), be->begin(), be->end());
   }
   for (HAttn& a : c->attns) {
+    if (a.kind != 0) continue;
     const std::string q = "denoise_fn." + a.name;
     const std::vector<float>*w1 = find_w(c, q + ".ca.fc1.weight"), *w2 = find_w(c, q + ".ca.fc2.weight"),
                             *w7 = find_w(c, q + ".sa.conv1.weight");
@@ -528,25 +610,46 @@ std::vector<float> linear(const std::vector<float>& w, const std::vector<float>&
 // Per-step bias tables: conv bias (+ res_conv bias) + FiLM(noise_level_t) (unet.py:22-54, 242-248)
 int build_bias_tables(fdsr_ctx* c) {
   const int T = c->T, inner = c->cfg.inner_channel;
-  const auto *w1 = find_w(c, "denoise_fn.noise_level_mlp.1.weight"), *b1 = find_w(c, "denoise_fn.noise_level_mlp.1.bias"),
-             *w3 = find_w(c, "denoise_fn.noise_level_mlp.3.weight"), *b3 = find_w(c, "denoise_fn.noise_level_mlp.3.bias");
-  if (!w1 || !b1 || !w3 || !b3) return fail(c, FDSR_E_NOTFOUND, "missing noise_level_mlp weights");
+  const bool sr3 = c->cfg.model == FDSR_MODEL_SR3;
+  // FastDiffSR embeds the noise level sqrt_alphas_cumprod_prev[t+1] (noise_level_mlp); the SR3 baseline embeds the
+  // integer step t itself (time_mlp, ddpm_modules/unet.py:19-33, 165-171; diffusion.py:178)
+  const std::string mlp = sr3 ? "denoise_fn.time_mlp" : "denoise_fn.noise_level_mlp";
+  const auto *w1 = find_w(c, mlp + ".1.weight"), *b1 = find_w(c, mlp + ".1.bias"), *w3 = find_w(c, mlp + ".3.weight"),
+             *b3 = find_w(c, mlp + ".3.bias");
+  if (!w1 || !b1 || !w3 || !b3) return fail(c, FDSR_E_NOTFOUND, "missing %s weights", mlp.c_str());
   const std::vector<double>& nl = c->tables["sqrt_alphas_cumprod_prev"];
+  const int count = inner / 2;
+  std::vector<float> inv_freq(count);
+  if (sr3) {
+    const auto* fr = find_w(c, "denoise_fn.time_mlp.0.inv_freq");  // registered buffer: part of the state_dict
+    for (int i = 0; i < count; ++i)
+      inv_freq[i] = (fr && int(fr->size()) == count) ? (*fr)[i] : expf(float(2 * i) * (-logf(10000.f) / float(inner)));
+  }
   std::vector<std::vector<float>> temb(T);
   for (int t = 0; t < T; ++t) {
-    const float level = float(nl[t + 1]);
-    const int count = inner / 2;
     std::vector<float> enc(inner);
-    for (int i = 0; i < count; ++i) {
-      const float step = float(i) / float(count);
-      const float e = level * expf(-logf(1e4f) * step);
-      enc[i] = sinf(e);
-      enc[count + i] = cosf(e);
+    if (sr3) {
+      for (int i = 0; i < count; ++i) {
+        const float e = float(t) * inv_freq[i];
+        enc[i] = sinf(e);
+        enc[count + i] = cosf(e);
+      }
+    } else {
+      const float level = float(nl[t + 1]);
+      for (int i = 0; i < count; ++i) {
+        const float step = float(i) / float(count);
+        const float e = level * expf(-logf(1e4f) * step);
+        enc[i] = sinf(e);
+        enc[count + i] = cosf(e);
+      }
     }
     std::vector<float> h = linear(*w1, *b1, enc);
     for (float& v : h) v = v / (1.0f + expf(-v));
     temb[t] = linear(*w3, *b3, h);
   }
+  std::vector<std::vector<float>> temb_sw = temb;  // swish(emb): input of the SR3 per-block Linear
+  for (auto& e : temb_sw)
+    for (float& v : e) v = v / (1.0f + expf(-v));
   size_t total = 0;
   for (HConv& k : c->convs) {
     k.bias_off = total;
@@ -570,7 +673,7 @@ int build_bias_tables(fdsr_ctx* c) {
       float* row = tab.data() + k.bias_off + size_t(t) * k.N;
       for (int n = 0; n < k.N; ++n) row[n] = base[n];
       if (fw) {
-        const std::vector<float> f = linear(*fw, *fb, temb[t]);
+        const std::vector<float> f = linear(*fw, *fb, k.film_swish ? temb_sw[t] : temb[t]);
         for (int n = 0; n < k.cout; ++n) row[n] += f[n];
       }
     }
@@ -627,6 +730,50 @@ bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bo
   return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// [B][HW][C] 16-bit token matrix (an NHWC activation seen as rows of C channels) as a rank-3 TMA tensor
+// {C, HW, B}, box {64 ch, rows, 1}, 128B swizzle: K-major (q, k) / MN-major (v) MMA operand tiles
+bool make_token_map(CUtensorMap* m, const void* ptr, int B, int HW, int C, int rows, bool bf16) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {cuuint64_t(C), cuuint64_t(HW), cuuint64_t(B)};
+  const cuuint64_t strides[2] = {cuuint64_t(C) * 2, cuuint64_t(HW) * C * 2};
+  const cuuint32_t box[3] = {64, cuuint32_t(rows), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr),
+             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T, int C>
+cudaError_t launch_attn_core_tc(const AttnParams& p, int B, int HW, cudaStream_t st);
+
+// SelfAttention cores of the SR3 baseline (16-bit modes): tensor maps of q / k / v at the reserved shape
+int upload_attn(fdsr_ctx* c) {
+  c->a_params.assign(c->attns.size(), AttnParams{});
+  const bool bf = c->cfg.dtype == FDSR_DTYPE_BF16;
+  for (size_t i = 0; i < c->attns.size(); ++i) {
+    const HAttn& a = c->attns[i];
+    if (a.kind != 1 || c->attn_ref) continue;
+    const HTensor& tq = c->tensors[a.tq];
+    const int HW = (c->H >> tq.level) * (c->W >> tq.level);
+    AttnParams& p = c->a_params[i];
+    if (!make_token_map(&p.q_map, c->d_ws + tq.off, c->B, HW, a.C, kAttnQ, bf) ||
+        !make_token_map(&p.k_map, c->d_ws + c->tensors[a.tk].off, c->B, HW, a.C, kAttnKB, bf) ||
+        !make_token_map(&p.v_map, c->d_ws + c->tensors[a.tv].off, c->B, HW, a.C, kAttnKB, bf))
+      return fail(c, FDSR_E_CUDA, "cuTensorMapEncodeTiled failed for the attention operands of %s", a.name.c_str());
+    p.out = c->d_ws + c->tensors[a.out].off;
+    p.HW = HW;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(float(a.C));
+    cudaError_t e = cudaErrorInvalidValue;  // B = 0: only sets the kernel's shared-memory attribute (not capturable)
+    if (a.C == 64) e = bf ? launch_attn_core_tc<__nv_bfloat16, 64>(p, 0, 0, 0) : launch_attn_core_tc<__half, 64>(p, 0, 0, 0);
+    else if (a.C == 128) e = bf ? launch_attn_core_tc<__nv_bfloat16, 128>(p, 0, 0, 0) : launch_attn_core_tc<__half, 128>(p, 0, 0, 0);
+    else if (a.C == 256) e = bf ? launch_attn_core_tc<__nv_bfloat16, 256>(p, 0, 0, 0) : launch_attn_core_tc<__half, 256>(p, 0, 0, 0);
+    if (e != cudaSuccess)
+      return fail(c, FDSR_E_CUDA, "SelfAttention with %d channels: %s", a.C, cudaGetErrorString(e));
+  }
+  return FDSR_OK;
 }
 
 // fp32 parity mode: layer descriptions for conv_f32_kernel / f32_gn_table_kernel
@@ -829,6 +976,8 @@ int upload_layers(fdsr_ctx* c) {
   }
   static_assert(sizeof(ConvLayer) <= 4000, "ConvLayer must fit the kernel parameter space");
   c->h_layers = L;
+  const int rc = upload_attn(c);
+  if (rc) return rc;
   c->layers_dirty = false;
   return FDSR_OK;
 }
@@ -907,8 +1056,49 @@ int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st) {
   return fail(c, FDSR_E_INVALID, "unsupported N=%d", k.N);
 }
 
+template <typename T, int C>
+cudaError_t launch_attn_core_tc(const AttnParams& p, int B, int HW, cudaStream_t st) {
+  static bool attr_set = false;  // (set outside stream capture: upload_layers calls this with B = 0 first)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_core_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnCfg<C>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (B == 0) return cudaSuccess;
+  attn_core_kernel<T, C><<<dim3((HW + kAttnQ - 1) / kAttnQ, B), kAttnQ, AttnCfg<C>::kSmemBytes, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <typename T>
-int launch_attn(fdsr_ctx* c, const HAttn& a, cudaStream_t st) {
+int launch_self_attn(fdsr_ctx* c, int ai, cudaStream_t st) {
+  const HAttn& a = c->attns[ai];
+  const HTensor& tq = c->tensors[a.tq];
+  const int HW = (c->H >> tq.level) * (c->W >> tq.level), C = a.C;
+  if constexpr (sizeof(T) == 2) {
+    if (!c->attn_ref) {
+      cudaError_t e = cudaErrorInvalidValue;
+      if (C == 64) e = launch_attn_core_tc<T, 64>(c->a_params[ai], c->B, HW, st);
+      else if (C == 128) e = launch_attn_core_tc<T, 128>(c->a_params[ai], c->B, HW, st);
+      else if (C == 256) e = launch_attn_core_tc<T, 256>(c->a_params[ai], c->B, HW, st);
+      if (e != cudaSuccess) return fail(c, FDSR_E_CUDA, "attention core launch failed: %s", cudaGetErrorString(e));
+      ++c->launches;
+      return FDSR_OK;
+    }
+  }
+  attn_core_ref_kernel<T><<<dim3((HW + 7) / 8, c->B), 256, 0, st>>>(
+      reinterpret_cast<const T*>(c->d_ws + tq.off), reinterpret_cast<const T*>(c->d_ws + c->tensors[a.tk].off),
+      reinterpret_cast<const T*>(c->d_ws + c->tensors[a.tv].off), reinterpret_cast<T*>(c->d_ws + c->tensors[a.out].off),
+      HW, C, 1.0f / sqrtf(float(C)));
+  CUDA_TRY(c, cudaGetLastError());
+  ++c->launches;
+  return FDSR_OK;
+}
+
+template <typename T>
+int launch_attn(fdsr_ctx* c, int ai, cudaStream_t st) {
+  const HAttn& a = c->attns[ai];
+  if (a.kind == 1) return launch_self_attn<T>(c, ai, st);
   const HTensor& ti = c->tensors[a.in];
   const HTensor& to = c->tensors[a.out];
   const int h = c->H >> ti.level, w = c->W >> ti.level, HW = h * w, C = a.C, R = C / 16;
@@ -946,7 +1136,7 @@ int unet_internal(fdsr_ctx* c, int t, cudaStream_t st) {
       reinterpret_cast<T*>(c->d_ws + c->tensors[c->t_xin].off), c->B, HW);
   ++c->launches;
   for (const HOp& op : c->ops) {
-    int rc = op.kind == 0 ? launch_conv<T>(c, op.idx, t, st) : launch_attn<T>(c, c->attns[op.idx], st);
+    int rc = op.kind == 0 ? launch_conv<T>(c, op.idx, t, st) : launch_attn<T>(c, op.idx, st);
     if (rc) return rc;
   }
   return FDSR_OK;
@@ -989,10 +1179,22 @@ int sample_enqueue(fdsr_ctx* c, const float* noise, float* trace, cudaStream_t s
     noise_fill_kernel<<<unsigned((numel / 4 + 255) / 256), 256, 0, st>>>(x, numel / 4, seed, uint32_t(T));
     ++c->launches;
   }
+  // FastDiffSR predicts the residual: frames and result go through res2img (diffusion.py:213-216, 275-281).
+  // The SR3 baseline predicts the image: frames are the raw x, the first frame is the conditioning image itself
+  // (ddpm_modules/diffusion.py:218-227).
+  const bool sr3 = c->cfg.model == FDSR_MODEL_SR3;
+  auto copy_frame = [&](const float* src, float* dst, size_t dst_stride) {  // B images of `per` floats
+    return cudaMemcpy2DAsync(dst, dst_stride * 4, src, size_t(per) * 4, size_t(per) * 4, size_t(B),
+                             cudaMemcpyDeviceToDevice, st);
+  };
   int frame = 0;
   if (trace) {
-    res2img_kernel<<<gb, 256, 0, st>>>(cond, cond, trace, per, per * nfr, B);
-    ++c->launches;
+    if (sr3) {
+      CUDA_TRY(c, copy_frame(cond, trace, size_t(per) * nfr));
+    } else {
+      res2img_kernel<<<gb, 256, 0, st>>>(cond, cond, trace, per, per * nfr, B);
+      ++c->launches;
+    }
     frame = 1;
   }
   const int inter = 1 | (T / 10);
@@ -1003,13 +1205,21 @@ int sample_enqueue(fdsr_ctx* c, const float* noise, float* trace, cudaStream_t s
     rc = posterior_launch(c, x, eps, z, t, x, numel, (!noise && t > 0) ? seed : nullptr, st);
     if (rc) return rc;
     if (trace && t % inter == 0) {
-      res2img_kernel<<<gb, 256, 0, st>>>(x, cond, trace + per * frame, per, per * nfr, B);
-      ++c->launches;
+      if (sr3) {
+        CUDA_TRY(c, copy_frame(x, trace + per * frame, size_t(per) * nfr));
+      } else {
+        res2img_kernel<<<gb, 256, 0, st>>>(x, cond, trace + per * frame, per, per * nfr, B);
+        ++c->launches;
+      }
       ++frame;
     }
   }
-  res2img_kernel<<<gb, 256, 0, st>>>(x, cond, sr, per, per, B);
-  ++c->launches;
+  if (sr3) {
+    CUDA_TRY(c, cudaMemcpyAsync(sr, x, size_t(numel) * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    res2img_kernel<<<gb, 256, 0, st>>>(x, cond, sr, per, per, B);
+    ++c->launches;
+  }
   CUDA_TRY(c, cudaGetLastError());
   return FDSR_OK;
 }
@@ -1105,6 +1315,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tma_in = !(e6 && e6[0] == '0');
     const char* e7 = getenv("FDSR_TWO_RINGS");
     c->two_rings = !(e7 && e7[0] == '0');
+    const char* e8 = getenv("FDSR_ATTN_REF");
+    c->attn_ref = e8 && e8[0] == '1';
   }
   if (cfg->dtype != FDSR_DTYPE_FP16 && cfg->dtype != FDSR_DTYPE_BF16 && cfg->dtype != FDSR_DTYPE_FP32) {
     delete c;
@@ -1159,8 +1371,7 @@ int fdsr_load_weights(fdsr_ctx* c, const char* const* names, const float* const*
     for (const HChunk& ch : k.chunks) {
       const auto* w = find_w(c, ch.wname);
       if (!w) return fail(c, FDSR_E_NOTFOUND, "state_dict is missing %s", ch.wname.c_str());
-      const bool is1x1 = ch.wname.find("res_conv") != std::string::npos;
-      if (w->size() % (size_t(k.cout) * (is1x1 ? 1 : 9)) != 0)
+      if (w->size() % (size_t(k.w_rows ? k.w_rows : k.cout) * ch.kk * ch.kk) != 0)
         return fail(c, FDSR_E_INVALID, "unexpected size for %s", ch.wname.c_str());
     }
   int rc = c->cfg.dtype == FDSR_DTYPE_FP32 ? pack_weights_f32(c)
@@ -1258,6 +1469,7 @@ int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
   // CLAM pools live in the per-forward zeroed region too
   int cmax = 0, lmin = 99;
   for (const HAttn& a : c->attns) {
+    if (a.kind != 0) continue;
     cmax = a.C > cmax ? a.C : cmax;
     lmin = c->tensors[a.in].level < lmin ? c->tensors[a.in].level : lmin;
   }
@@ -1349,7 +1561,9 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
   // the Philox seed is read from device memory, so one captured graph serves every seed
   set_seed_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint64_t*>(c->d_ws + c->off_seed), seed);
   ++c->launches;
-  const bool want_graph = c->use_graph;
+  // a T = 1000 schedule would be a graph of ~10^5 nodes: long schedules are enqueued directly (the host runs
+  // far ahead of the device: ~0.3 ms of launch calls per ~5 ms UNet step)
+  const bool want_graph = c->use_graph && c->T <= 100;
   if (want_graph) {
     if (c->layers_dirty) {
       rc = upload_layers(c);
@@ -1390,8 +1604,11 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
     // launches per replay: recompute deterministically
     int per_unet = 1;
     for (const HOp& op : c->ops)
-      per_unet += op.kind != 0 ? 4 : ((c->cfg.dtype == FDSR_DTYPE_FP32 && c->convs[op.idx].gn_C) ? 2 : 1);
-    c->launches += int64_t(c->T) * (per_unet + 1) + 1 + (noise ? 0 : 1) + (trace ? fdsr_trace_frames(c) : 0);
+      per_unet += op.kind != 0 ? (c->attns[op.idx].kind == 0 ? 4 : 1)
+                               : ((c->cfg.dtype == FDSR_DTYPE_FP32 && c->convs[op.idx].gn_C) ? 2 : 1);
+    const bool sr3 = c->cfg.model == FDSR_MODEL_SR3;  // (its frames and result are copies, not kernels)
+    c->launches += int64_t(c->T) * (per_unet + 1) + (sr3 ? 0 : 1) + (noise ? 0 : 1) +
+                   ((trace && !sr3) ? fdsr_trace_frames(c) : 0);
   } else {
     rc = sample_enqueue(c, noise, trace, st);
     if (rc) return rc;
@@ -1532,7 +1749,10 @@ int32_t fdsr_debug_num_ops(const fdsr_ctx* c) { return c ? int32_t(c->ops.size()
 const char* fdsr_debug_op_name(const fdsr_ctx* c, int32_t i) {
   if (!c || i < 0 || i >= int(c->ops.size())) return nullptr;
   const HOp& op = c->ops[i];
-  return op.kind == 0 ? c->convs[op.idx].name.c_str() : "mid.0.clam_slam";
+  if (op.kind == 0) return c->convs[op.idx].name.c_str();
+  static thread_local std::string nm;
+  nm = c->attns[op.idx].name + (c->attns[op.idx].kind == 0 ? ".clam_slam" : ".attn.core");
+  return nm.c_str();
 }
 double fdsr_debug_op_flops(const fdsr_ctx* c, int32_t i) {
   if (!c || i < 0 || i >= int(c->ops.size()) || c->ops[i].kind != 0) return 0.0;
@@ -1563,9 +1783,9 @@ int fdsr_debug_profile_unet(fdsr_ctx* c, int32_t t, int32_t reps, float* ms_out_
     for (int i = 0; i < nops; ++i) {
       const HOp& op = c->ops[i];
       CUDA_TRY(c, cudaEventRecord(ev[(size_t(r) * nops + i) * 2], st));
-      if (f32) rc = op.kind == 0 ? launch_conv<float>(c, op.idx, t, st) : launch_attn<float>(c, c->attns[op.idx], st);
+      if (f32) rc = op.kind == 0 ? launch_conv<float>(c, op.idx, t, st) : launch_attn<float>(c, op.idx, st);
       else if (op.kind == 0) rc = bf ? launch_conv<__nv_bfloat16>(c, op.idx, t, st) : launch_conv<__half>(c, op.idx, t, st);
-      else rc = bf ? launch_attn<__nv_bfloat16>(c, c->attns[op.idx], st) : launch_attn<__half>(c, c->attns[op.idx], st);
+      else rc = bf ? launch_attn<__nv_bfloat16>(c, op.idx, st) : launch_attn<__half>(c, op.idx, st);
       if (rc) return rc;
       CUDA_TRY(c, cudaEventRecord(ev[(size_t(r) * nops + i) * 2 + 1], st));
     }

@@ -46,7 +46,7 @@ enum OutMode : int32_t {
 struct ConvChunk {
   int32_t src;        // index into ConvLayer::src
   int32_t c0;         // first channel inside the source tensor
-  int32_t gn;         // 1: GroupNorm+Swish with scale/shift table entries [vc0, vc0+64)
+  int32_t gn;         // 1: GroupNorm+Swish with scale/shift table entries [vc0, vc0+64); 2: GroupNorm only (no activation)
   int32_t vc0;        // channel offset on the virtual (concatenated) GroupNorm axis
   int32_t pix_delta;  // extra source pixel offset (parity plane of the space-to-depth view)
   int32_t ntaps;

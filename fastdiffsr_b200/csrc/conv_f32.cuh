@@ -20,7 +20,7 @@ struct F32Chunk {
   const float* src;   // NHWC fp32 source tensor
   int32_t C, H, W;    // source channels / spatial size
   int32_t c0, nch;    // channels [c0, c0 + nch) of the source feed this chunk (nch <= 64)
-  int32_t gn, vc0;    // GroupNorm + Swish with table entries [vc0, vc0 + nch)
+  int32_t gn, vc0;    // GroupNorm (+ Swish when gn = 1) with table entries [vc0, vc0 + nch)
   int32_t pa, pb;     // space-to-depth parity plane (kModeS2D)
   int32_t ntaps;
   int8_t dy[kMaxTaps], dx[kMaxTaps];  // tap offsets in the conv's input space (block space for kModeS2D)
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const __grid_constant__ F
           if (ck.gn) {
             const float2 g = L.gn_tab[size_t(b) * L.gn_C + ck.vc0 + ci0 + ci];
             const float u = fmaf(v, g.x, g.y);
-            v = u / (1.0f + expf(-u));
+            v = ck.gn == 2 ? u : u / (1.0f + expf(-u));  // gn = 2: GroupNorm without activation (attention norm)
           }
         }
         Ps[ci][pos] = v;

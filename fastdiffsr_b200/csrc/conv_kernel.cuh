@@ -156,6 +156,32 @@ __device__ __forceinline__ uint4 gn_swish_unit(uint4 o, const uint4& hsc, const 
   return make_uint4(r4[0], r4[1], r4[2], r4[3]);
 }
 
+// GroupNorm scale/shift only (the SelfAttention norm of the SR3 baseline has no activation,
+// ddpm_modules/unet.py:105,115): y = x*sc + sh; the packed-half table holds sc/2, sh/2, so y = h + h.
+template <typename T, bool kFast>
+__device__ __forceinline__ uint4 gn_affine_unit(uint4 o, const uint4& hsc, const uint4& hsh, const float (&sc)[8],
+                                                const float (&sh)[8]) {
+  if (kFast) {
+    const uint32_t w4[4] = {o.x, o.y, o.z, o.w}, s4[4] = {hsc.x, hsc.y, hsc.z, hsc.w}, b4[4] = {hsh.x, hsh.y, hsh.z, hsh.w};
+    uint32_t r4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint32_t h;
+      asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(w4[e]), "r"(s4[e]), "r"(b4[e]));
+      asm("add.rn.f16x2 %0, %1, %1;" : "=r"(r4[e]) : "r"(h));
+    }
+    return make_uint4(r4[0], r4[1], r4[2], r4[3]);
+  }
+  const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+  uint32_t r4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = Cvt<T>::unpack(w4[e]);
+    r4[e] = Cvt<T>::pack(fmaf(f.x, sc[2 * e], sh[2 * e]), fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
+  }
+  return make_uint4(r4[0], r4[1], r4[2], r4[3]);
+}
+
 // true in exactly one lane of a fully converged warp (elect.sync keeps the uniform datapath usable)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -900,9 +926,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
 #pragma unroll
             for (int i = 0; i < kMaxUnits; ++i)
               if ((vmask >> i) & 1u) rv[i] = lds128(a0 + i * (40 * 128));
+            if (ck.gn == 1) {
 #pragma unroll
-            for (int i = 0; i < kMaxUnits; ++i)
-              if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_swish_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
+              for (int i = 0; i < kMaxUnits; ++i)
+                if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_swish_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
+            } else {  // GroupNorm without activation
+#pragma unroll
+              for (int i = 0; i < kMaxUnits; ++i)
+                if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_affine_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
+            }
             fence_proxy_async_smem();
           }
           PROF_MARK(3);
@@ -1006,7 +1038,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           for (int i = 0; i < kMaxUnits; ++i) {
             if ((stmask >> i) & 1u) {
               uint4 o = rv[i];
-              if ((tmask >> i) & 1u) o = gn_swish_unit<T, kFast>(o, hsc, hsh, sc, sh);
+              if ((tmask >> i) & 1u)
+                o = ck.gn == 1 ? gn_swish_unit<T, kFast>(o, hsc, hsh, sc, sh) : gn_affine_unit<T, kFast>(o, hsc, hsh, sc, sh);
               sts128(dst0 + uint32_t((i * kProdThreads) >> lg) * 16, o);
             }
           }

@@ -9,6 +9,11 @@ state_dict compatibility.  Differences, all deliberate:
   * Gaussian noise may be injected (`noise=`) for parity, else it comes from the library's
     counter-based generator seeded from torch's global RNG (the reference is unseeded, F7);
   * training (`forward` -> p_losses) is out of scope for this path and raises.
+
+The same class serves the SR3 baseline (which_model_G == "ddpm", model/ddpm_modules/diffusion.py:79-298) when
+its denoise_fn is an SR3UNet: the UNet is conditioned on the integer step t (not on a noise level), the image
+itself is predicted (no res2img), and `super_resolution` returns `ret_img[-1]` — for B = 1 the (3,H,W) image
+without the batch axis, exactly as the reference does (ddpm diffusion.py:228-231); B > 1 returns (B,3,H,W).
 """
 from __future__ import annotations
 
@@ -69,6 +74,7 @@ class GaussianDiffusion(nn.Module):
         self.loss_type = loss_type
         self.conditional = conditional
         self.compute_dtype = dtype
+        self.sr3 = getattr(denoise_fn, "cfg", {}).get("model") == "ddpm"
         self._engine = None
         self._weights_dirty = True
         self._betas64 = None
@@ -170,7 +176,8 @@ class GaussianDiffusion(nn.Module):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         if not continous:
-            return eng.sample(x_in, noise=noise, seed=seed)
+            sr = eng.sample(x_in, noise=noise, seed=seed)
+            return sr[0] if (self.sr3 and sr.shape[0] == 1) else sr  # SR3: ret_img[-1] drops the batch axis
         sr, tr = eng.sample(x_in, noise=noise, seed=seed, trace=True)
         return tr.reshape(-1, *tr.shape[2:])  # B=1: (1+frames,3,H,W) exactly as the reference
 

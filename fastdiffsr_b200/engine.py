@@ -35,6 +35,19 @@ class Engine:
             cfg.channel_mults[i] = m
         cfg.res_blocks = unet_cfg["res_blocks"]
         cfg.dtype = _DTYPES[dtype]
+        # which_model_G: "fastdiffsr" (default) or "ddpm" = the SR3 baseline, whose ResnetBlocks carry SelfAttention
+        # where the resolution of the *configured* image_size is in attn_res (ddpm_modules/unet.py:184, 211)
+        self.model = unet_cfg.get("model", "fastdiffsr")
+        if self.model not in ("fastdiffsr", "ddpm"):
+            raise FdsrError(f"unknown model {self.model!r}")
+        cfg.model = _lib.MODEL_SR3 if self.model == "ddpm" else _lib.MODEL_FASTDIFFSR
+        cfg.attn_levels = 0
+        if self.model == "ddpm":
+            res = int(unet_cfg.get("image_size", 256))
+            for i in range(len(mults)):
+                if res in list(unet_cfg["attn_res"]):
+                    cfg.attn_levels |= 1 << i
+                res //= 2
         self.dtype = dtype
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -4,19 +4,19 @@ from __future__ import annotations
 import os
 
 from .diffusion import GaussianDiffusion
-from .unet import UNet
+from .unet import SR3UNet, UNet
 
 
 def define_G(opt):
     model_opt = opt["model"]
     which = model_opt["which_model_G"]
-    if which != "fastdiffsr":
-        raise NotImplementedError(f"which_model_G={which!r}: only the 'fastdiffsr' generator is on the B200 path "
-                                  "(ddpm / tesr / gdp are the paper's comparison baselines)")
+    if which not in ("fastdiffsr", "ddpm"):
+        raise NotImplementedError(f"which_model_G={which!r}: the B200 path implements 'fastdiffsr' and the SR3 baseline "
+                                  "'ddpm' (tesr / gdp are further comparison baselines of the paper)")
     if ("norm_groups" not in model_opt["unet"]) or model_opt["unet"]["norm_groups"] is None:
         model_opt["unet"]["norm_groups"] = 32
     u = model_opt["unet"]
-    model = UNet(in_channel=u["in_channel"], out_channel=u["out_channel"], norm_groups=u["norm_groups"],
+    model = (SR3UNet if which == "ddpm" else UNet)(in_channel=u["in_channel"], out_channel=u["out_channel"], norm_groups=u["norm_groups"],
                  inner_channel=u["inner_channel"], channel_mults=u["channel_multiplier"], attn_res=u["attn_res"],
                  res_blocks=u["res_blocks"], dropout=u["dropout"], image_size=model_opt["diffusion"]["image_size"])
     dtype = model_opt.get("compute_dtype") if hasattr(model_opt, "get") else None

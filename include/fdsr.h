@@ -38,6 +38,10 @@ extern "C" {
 
 #define FDSR_MAX_LEVELS 8
 
+#define FDSR_MODEL_FASTDIFFSR 0 /* which_model_G = "fastdiffsr": model/fastdiffsr_modules (noise-level FiLM, CLAM/SLAM) */
+#define FDSR_MODEL_SR3 1        /* which_model_G = "ddpm": the SR3 comparison baseline, model/ddpm_modules (time
+                                   embedding, SelfAttention); it predicts the image itself (no res2img) */
+
 typedef struct fdsr_ctx fdsr_ctx;
 
 /* UNet hyper-parameters: opt['model']['unet'] consumed by define_G (model/networks.py:82-119)
@@ -51,6 +55,9 @@ typedef struct fdsr_config {
   int32_t channel_mults[FDSR_MAX_LEVELS];
   int32_t res_blocks;     /* 2 */
   int32_t dtype;          /* FDSR_DTYPE_* */
+  int32_t model;          /* FDSR_MODEL_* (networks.py:84-91) */
+  int32_t attn_levels;    /* FDSR_MODEL_SR3: bit l set = the ResnetBlocks of resolution level l carry SelfAttention,
+                             i.e. (image_size >> l) is in attn_res (ddpm_modules/unet.py:184, 211); mid[0] always does */
 } fdsr_config;
 
 /* Replaces UNet.__init__ + GaussianDiffusion.__init__ (diffusion.py:80-99): builds the layer plan. */
