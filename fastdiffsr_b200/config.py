@@ -53,6 +53,12 @@ _SHAPES = {
     "sr_fastdiffsr_train_32_256": (32, 256, "dataset/Train_32_256", "dataset/Test_Potsdam_32_256"),
     "sr_fastdiffsr_infer_x4": (128, 512, "dataset/Train_64_256", "dataset/UCM_128_512"),
     "sr_fastdiffsr_infer_128_512": (128, 512, "dataset/Train_64_256", "dataset/UCM_128_512"),
+    # the SR3 comparison baseline (which_model_G = "ddpm", config/sr_ddpm_*.json)
+    "sr_ddpm_test_64_256": (64, 256, "dataset/Train_64_256", "dataset/Test_Toronto_64_256"),
+    "sr_ddpm_train_64_256": (64, 256, "dataset/Train_64_256", "dataset/Test_Potsdam_64_256"),
+    "sr_ddpm_test_32_256": (32, 256, "dataset/Train_32_256", "dataset/Test_Toronto_32_256"),
+    "sr_ddpm_train_32_256": (32, 256, "dataset/Train_32_256", "dataset/Test_Potsdam_32_256"),
+    "sr_ddpm_infer_x4": (128, 512, "dataset/Train_64_256", "dataset/UCM_128_512"),
 }
 
 
@@ -65,7 +71,9 @@ def default_config(name: str = "sr_fastdiffsr_test_64_256", phase: str = "val", 
     if name not in _SHAPES:
         raise KeyError(f"unknown config {name!r}; known: {sorted(_SHAPES)}")
     lres, rres, train_root, val_root = _SHAPES[name]
-    sched = dict(schedule="linear_cosine", n_timestep=20, linear_start=1e-6, linear_end=1e-2)
+    sr3 = name.startswith("sr_ddpm")
+    sched = (dict(schedule="linear", n_timestep=1000, linear_start=1e-4, linear_end=2e-2) if sr3
+             else dict(schedule="linear_cosine", n_timestep=20, linear_start=1e-6, linear_end=1e-2))
     # the x4 train/infer configs condition on 64->256 training crops; inference runs fully convolutionally
     train_l = 64 if lres == 128 else lres
     opt = {
@@ -77,8 +85,9 @@ def default_config(name: str = "sr_fastdiffsr_test_64_256", phase: str = "val", 
                     "l_resolution": lres, "r_resolution": rres},
         },
         "model": {
-            "which_model_G": "fastdiffsr", "finetune_norm": False,
-            "unet": {"in_channel": 6, "out_channel": 3, "inner_channel": 64, "channel_multiplier": [1, 2, 4, 4],
+            "which_model_G": "ddpm" if sr3 else "fastdiffsr", "finetune_norm": False,
+            "unet": {"in_channel": 6, "out_channel": 3, "inner_channel": 64,
+                     "channel_multiplier": [1, 1, 2, 2, 4, 4] if sr3 else [1, 2, 4, 4],
                      "attn_res": [16], "res_blocks": 2, "dropout": 0.2},
             "beta_schedule": {"train": dict(sched), "val": dict(sched)},
             "diffusion": {"image_size": 256, "channels": 3, "conditional": True},

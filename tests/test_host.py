@@ -73,9 +73,35 @@ def test_define_G_surface_and_state_dict(oracle, golden_dir):
     netG.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], "cpu")  # re-entrant like the reference
 
 
+def test_sr3_define_G_surface_and_configs(oracle):
+    """which_model_G = 'ddpm' (the SR3 baseline): config defaults equal the reference JSONs, state_dict surface
+    equals the reference's (421 tensors incl. the time_mlp.0.inv_freq buffer), no CPU fallback."""
+    for name in ("sr_ddpm_test_64_256", "sr_ddpm_test_32_256", "sr_ddpm_infer_x4"):
+        mine = default_config(name)
+        assert mine["model"]["which_model_G"] == "ddpm" and mine["model"]["beta_schedule"]["val"]["n_timestep"] == 1000
+        if os.path.isdir(REF_CFG):
+            ref = load_config(os.path.join(REF_CFG, name + ".json"))
+            for key in ("unet", "beta_schedule", "diffusion", "which_model_G"):
+                assert ref["model"][key] == mine["model"][key], (name, key)
+    opt = default_config("sr_ddpm_test_64_256")
+    netG = F.define_G(opt)
+    assert isinstance(netG.denoise_fn, F.SR3UNet) and netG.sr3
+    keys = [(k, tuple(v.shape)) for k, v in netG.state_dict().items()]
+    assert keys == [(k, s) for k, s, _, _ in oracle.sr3_state_dict_spec(oracle.SR3_UNET, 256)] and len(keys) == 421
+    sd = oracle.make_state_dict(oracle.SR3_UNET, seed=3, spec=oracle.sr3_state_dict_spec(oracle.SR3_UNET, 256))
+    assert torch.equal(sd["denoise_fn.time_mlp.0.inv_freq"], netG.state_dict()["denoise_fn.time_mlp.0.inv_freq"])
+    netG.load_state_dict(sd, strict=True)
+    netG.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], "cpu")
+    assert netG.num_timesteps == 1000
+    tab = oracle.schedule_tables(oracle.make_beta_schedule(**oracle.SR3_SCHEDULE))
+    assert np.array_equal(netG.posterior_mean_coef1.numpy(), tab["posterior_mean_coef1"].astype(np.float32))
+    with pytest.raises(F.FdsrError):
+        netG.super_resolution(torch.zeros(1, 3, 64, 64), False)
+
+
 def test_other_generators_and_training_rejected():
     opt = default_config()
-    opt["model"]["which_model_G"] = "ddpm"
+    opt["model"]["which_model_G"] = "tesr"
     with pytest.raises(NotImplementedError):
         F.define_G(opt)
     with pytest.raises(NotImplementedError):

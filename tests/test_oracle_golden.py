@@ -64,6 +64,43 @@ def test_unet_and_sampler_match_reference(oracle, schedule, golden_dir, tag):
     assert np.abs(src.numpy() - g["sr_continous"]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("image_size", [256, 64])
+def test_sr3_unet_and_sampler_match_reference(oracle, golden_dir, image_size):
+    """SR3 baseline restatement (ddpm_modules) against the reference's outputs (tests/golden/sr3_*.npz)."""
+    import json
+    g = np.load(os.path.join(golden_dir, f"sr3_{image_size}.npz"))
+    cfg = dict(oracle.SR3_UNET)
+    spec = oracle.sr3_state_dict_spec(cfg, image_size)
+    assert len(spec) == 421
+    sd = oracle.make_state_dict(cfg, seed=int(g["seed"]), gn_jitter=float(g["gn_jitter"]), spec=spec)
+    x6 = torch.from_numpy(g["x6"].astype(np.float32))
+    for i, t in enumerate(g["steps"][:1] if image_size == 256 else g["steps"]):
+        eps = oracle.sr3_unet_forward(sd, cfg, x6, torch.full((x6.shape[0],), int(t), dtype=torch.long), image_size)
+        assert np.abs(eps.numpy() - g["eps"][i]).max() <= 1e-5
+    if image_size == 256:
+        return  # (the 128x128 sampler costs ~10 s of CPU; the 64x64 fixture covers the loop)
+    tab = oracle.schedule_tables(oracle.make_beta_schedule(**json.loads(str(g["sched"]))))
+    cond = torch.from_numpy(g["cond"])
+    H = cond.shape[-1]
+    noises = torch.randn(12, 1, 3, H, H, generator=torch.Generator().manual_seed(int(g["noise_seed"])))
+    assert abs(float(noises.double().sum()) - float(g["noise_sum"])) < 1e-6
+    sr = oracle.sr3_sample_loop(sd, cfg, tab, cond, noises, image_size, False)
+    assert np.abs(sr[0].numpy() - g["sr"]).max() <= 1e-4
+    src = oracle.sr3_sample_loop(sd, cfg, tab, cond, noises, image_size, True)
+    assert tuple(src.shape) == (13, 3, H, H)
+    assert np.abs(src[::4].numpy() - g["sr_continous"]).max() <= 1e-4
+
+
+def test_sr3_attention_layout(oracle):
+    """SelfAttention flags follow the configured image_size, not the input (ddpm_modules/unet.py:184, 211)."""
+    for image_size, level in ((256, 4), (64, 2), (512, 5)):
+        downs, mid, ups, last = oracle.sr3_unet_layers(oracle.SR3_UNET, image_size)
+        flagged = [e[1] for e in downs + ups if e[0] == "res" and e[4]]
+        assert len(flagged) == 5 and mid[0][4] and not mid[1][4] and last == 64
+        widths = [64, 64, 128, 128, 256, 256]
+        assert all(e[3] == widths[level] for e in downs + ups if e[0] == "res" and e[4])
+
+
 def test_film_table_matches_forward(oracle, schedule):
     cfg = dict(oracle.DEFAULT_UNET)
     sd = oracle.make_state_dict(cfg, seed=1)
