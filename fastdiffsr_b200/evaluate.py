@@ -68,6 +68,8 @@ def evaluate(netG, dataset, batch_size=16, scale=4, result_path=None, save_ext="
         else:
             _, cond = eng.bicubic_u8(batch["LR"].to(dev, non_blocking=True), H, W, want_u8=False)
         sr = netG.super_resolution(cond, False, seed=seed + 7919 * (start + bi * loader.bs))
+        if sr.dim() == 3:   # the SR3 baseline returns ret_img[-1] without the batch axis for a single image
+            sr = sr[None]
         m_bic = eng.metrics_u8(cond, hr, scale)
         m_sr = eng.metrics_u8(sr, hr, scale)
         acc[0:4] += m_bic.sum(0)

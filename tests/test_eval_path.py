@@ -149,3 +149,21 @@ def test_batched_evaluation_loop(net, oracle, tmp_path):
     res2 = evaluate(net, D.LRHRDataset(root2, "img", 16, 64), batch_size=5, scale=4, seed=3)
     for k in ("mse", "psnr", "ssim", "ergas"):
         assert res2["bic_" + k] == pytest.approx(res["bic_" + k], rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_batched_evaluation_loop_sr3_baseline(oracle, tmp_path):
+    """The same validation loop with which_model_G = 'ddpm' (SR3 baseline; short schedule, 5 images in batches
+    of 2 so that the last call has a single image and returns the reference's batch-less (3,H,W) tensor)."""
+    from fastdiffsr_b200.evaluate import evaluate
+    opt = F.config.default_config("sr_ddpm_test_64_256")
+    torch.manual_seed(0)
+    netG = F.define_G(opt).to("cuda")
+    netG.set_new_noise_schedule(dict(schedule="linear", n_timestep=6, linear_start=1e-4, linear_end=0.4), "cuda")
+    root = _make_dataset(str(tmp_path / "ds"), n=5, l=16, r=64, with_sr=False)
+    ds = D.LRHRDataset(root, "img", 16, 64)
+    res = evaluate(netG.eval(), ds, batch_size=2, scale=4, seed=3)
+    assert res["n"] == 5 and all(np.isfinite(res[k]) for k in res if k != "n")
+    res_b = evaluate(netG, ds, batch_size=5, scale=4, seed=3)
+    for k in ("mse", "psnr", "ssim", "ergas"):
+        assert res_b["bic_" + k] == pytest.approx(res["bic_" + k], rel=1e-12)

@@ -42,6 +42,8 @@ struct Params {
   int a_shift; // byte offset of the A image inside shared memory (layout 4)
   int reps;    // MMA repetitions (timing)
   int two_acc; // alternate two accumulators sharing B (timing)
+  int ws;      // 1: tcgen05.mma.ws with the B operand latched in collector b0 (fill on the first accumulator, lastuse on
+               //    the second); 2: .ws fill on every MMA (no reuse)
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
@@ -93,11 +95,26 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
         bd[ks] = make_desc_nosw(b0 + (2 * ks) * p.N * 16, p.N * 16, 128);
       }
     }
-    const uint32_t tmem2 = (p.two_acc && p.N <= 128) ? tmem + 128 : tmem;
+    const uint32_t tmem2 = ((p.two_acc || p.ws) && p.N <= 128) ? tmem + 128 : tmem;
     t0 = clock64();
-    if (p.reps == 1) {
+    if (p.reps == 1 && p.ws) {
+#pragma unroll
+      for (int ks = 0; ks < KTOT / 16; ++ks) {  // both accumulators get the same product (checked below on tmem)
+        umma_f16_ws<0>(tmem2, ad[ks], bd[ks], idesc, ks != 0);
+        umma_f16_ws<1>(tmem, ad[ks], bd[ks], idesc, ks != 0);
+      }
+    } else if (p.reps == 1) {
 #pragma unroll
       for (int ks = 0; ks < KTOT / 16; ++ks) umma_f16(tmem, ad[ks], bd[ks], idesc, ks != 0);
+    } else if (p.ws) {
+      for (int r = 0; r < p.reps; ++r) {
+#pragma unroll
+        for (int ks = 0; ks < KTOT / 16; ++ks) {
+          umma_f16_ws<0>(tmem, ad[ks], bd[ks], idesc, 1);
+          if (p.ws == 1) umma_f16_ws<1>(tmem2, ad2[ks], bd[ks], idesc, 1);
+          else umma_f16_ws<0>(tmem2, ad2[ks], bd[ks], idesc, 1);
+        }
+      }
     } else {
       for (int r = 0; r < p.reps; ++r) {
 #pragma unroll
@@ -219,7 +236,7 @@ int main() {
         CK(cudaMalloc(&dc, 8));
         CK(cudaMemcpy(da, aimg.data(), a_bytes, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(db, bimg.data(), b_bytes, cudaMemcpyHostToDevice));
-        Params p{da, db, dd, dc, a_bytes, b_bytes, N, fmt, layout, a_shift, 1, 0};
+        Params p{da, db, dd, dc, a_bytes, b_bytes, N, fmt, layout, a_shift, 1, 0, 0};
         size_t smem = ((a_shift + a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
         probe_kernel<<<1, 128, smem>>>(p);
         CK(cudaDeviceSynchronize());
@@ -244,9 +261,37 @@ int main() {
         CK(cudaMemcpy(&cyc2, dc, 8, cudaMemcpyDeviceToHost));
         bool ok = maxerr < 1e-3;
         if (!ok) ++fails;
-        printf("layout=%d fmt=%s N=%3d maxerr=%.3e %s  cycles/MMA(K=16)=%.1f two-acc=%.1f (ideal %d)\n", layout,
+        // weight-stationary form (N <= 128 so that two accumulators fit the 256 allocated columns)
+        double wserr = -1.0;
+        long long cyc3 = 0, cyc4 = 0;
+        if (N <= 128 && fmt == 0) {
+          p.reps = 1;
+          p.two_acc = 0;
+          p.ws = 1;
+          probe_kernel<<<1, 128, smem>>>(p);
+          CK(cudaDeviceSynchronize());
+          CK(cudaMemcpy(D.data(), dd, 128 * N * 4, cudaMemcpyDeviceToHost));
+          wserr = 0;
+          for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < N; ++n) {
+              double ref = 0;
+              for (int k = 0; k < KTOT; ++k) ref += (double)A[m * KTOT + k] * B[(size_t)n * KTOT + k];
+              wserr = fmax(wserr, fabs(ref - D[m * N + n]));
+            }
+          p.reps = 256;
+          probe_kernel<<<1, 128, smem>>>(p);
+          CK(cudaDeviceSynchronize());
+          CK(cudaMemcpy(&cyc3, dc, 8, cudaMemcpyDeviceToHost));
+          p.ws = 2;
+          probe_kernel<<<1, 128, smem>>>(p);
+          CK(cudaDeviceSynchronize());
+          CK(cudaMemcpy(&cyc4, dc, 8, cudaMemcpyDeviceToHost));
+          if (wserr > 1e-3) ++fails;
+        }
+        printf("layout=%d fmt=%s N=%3d maxerr=%.3e %s  cycles/MMA(K=16)=%.1f two-acc=%.1f (ideal %d)  ws: err=%.3e "
+               "two-acc fill+lastuse=%.1f fill+fill=%.1f\n", layout,
                fmt ? "bf16" : "fp16", N, maxerr, ok ? "OK" : "FAIL", cyc / (256.0 * 4),
-               cyc2 / (256.0 * 8), N / 2);
+               cyc2 / (256.0 * 8), N / 2, wserr, cyc3 / (256.0 * 8), cyc4 / (256.0 * 8));
         cudaFree(da);
         cudaFree(db);
         cudaFree(dd);
