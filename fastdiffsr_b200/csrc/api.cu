@@ -53,6 +53,7 @@ struct HConv {
   std::vector<std::string> bias_names;
   std::string film_name;
   int resid = -1, out = -1, out_mode = kOutAct, out_c = 0;
+  int phases = 1;            // 4: nearest-x2 upsample + 3x3 conv as four 2x2 convs on the low-resolution input (see add_up)
   int w_n0 = 0, w_rows = 0;  // this launch uses rows [w_n0, w_n0 + cout) of a weight tensor with w_rows rows (0 = cout)
   bool film_swish = false;   // FiLM vector = Linear(swish(emb)) (SR3 ResnetBlock.mlp) instead of Linear(emb)
   // device-side resources
@@ -107,6 +108,7 @@ struct fdsr_ctx {
   std::vector<F32Layer> f_layers;   // fp32 parity mode: the same plan for conv_f32_kernel
   std::vector<F32GnArgs> f_gn;
   std::vector<AttnParams> a_params;  // per HAttn of kind 1 (16-bit modes)
+  bool up_phases = true;             // FDSR_UP_PHASES=0: nearest-upsample convs gather a 2x patch and run all nine taps
   bool attn_ref = false;             // FDSR_ATTN_REF=1: CUDA-core attention core in the 16-bit modes too
   float* d_weights32 = nullptr;     // fp32 parity mode weights: per conv, per chunk [tap][ci][N]
   std::vector<size_t> w32_off;      // per conv (floats)
@@ -414,13 +416,25 @@ int build_plan(fdsr_ctx* c) {
       const int to = add_tensor(c, nm, pre, level - 1, true);
       HConv k;
       k.name = nm;
-      k.mode = kModeUp2x;
       k.N = pad_n(pre);
       k.cout = pre;
       k.nsrc = 1;
       k.src[0] = cur;
-      for (int c0 = 0; c0 < pre; c0 += 64)
-        k.chunks.push_back({0, c0, 0, 0, -1, taps3x3(), "denoise_fn." + nm + ".conv.weight", c0, 64});
+      // Upsample (unet.py:66-74): nearest x2, then conv3x3.  Output pixel (2Y+py, 2X+px) only ever sees the 2x2
+      // low-resolution neighbourhood rows {Y-1+py, Y+py} x cols {X-1+px, X+px}: the three taps of a row/column that
+      // fall on the same source pixel are added up front (pack_weights), so each output parity is a 2x2 conv on
+      // the low-resolution tensor -- 4 instead of 9 MACs per weight, TMA-fed like every other stride-1 layer.
+      // An exact identity up to the rounding of the summed weights; the fp32 parity mode keeps the nine-tap form.
+      k.phases = (c->up_phases && g.dtype != FDSR_DTYPE_FP32 && pre >= 128) ? 4 : 1;
+      k.mode = k.phases == 4 ? kModeNormal : kModeUp2x;
+      for (int c0 = 0; c0 < pre; c0 += 64) {
+        if (k.phases == 4)
+          k.chunks.push_back({0, c0, 0, 0, -1,
+                              {{0, 0, 0}, {0, 1, 1}, {1, 0, kPatchW}, {1, 1, kPatchW + 1}},  // (ry, rx, patch position)
+                              "denoise_fn." + nm + ".conv.weight", c0, 64});
+        else
+          k.chunks.push_back({0, c0, 0, 0, -1, taps3x3(), "denoise_fn." + nm + ".conv.weight", c0, 64});
+      }
       k.bias_names = {"denoise_fn." + nm + ".conv.bias"};
       k.out = to;
       c->convs.push_back(k);
@@ -468,8 +482,8 @@ int build_plan(fdsr_ctx* c) {
     if (int(k.chunks.size()) > kMaxChunks) return fail(c, FDSR_E_INVALID, "layer %s: too many chunks", k.name.c_str());
     if (k.gn_C > kMaxGnC) return fail(c, FDSR_E_INVALID, "layer %s: GroupNorm width %d > %d", k.name.c_str(), k.gn_C, kMaxGnC);
     const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
-    double macs = 0.0;
-    for (const HChunk& ch : k.chunks) macs += double(ch.taps.size()) * ch.creal;
+    double macs = 0.0;  // algorithmic: a phase layer is accounted as the nine-tap conv it replaces
+    for (const HChunk& ch : k.chunks) macs += double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
     fl += 2.0 * macs * k.cout / double(1 << (2 * lvl));
   }
   c->flops_per_px = fl;
@@ -494,11 +508,12 @@ int pack_weights(fdsr_ctx* c) {
   size_t total = 0;
   for (HConv& k : c->convs) {
     k.w_off = total;
-    for (const HChunk& ch : k.chunks) total += ch.taps.size() * size_t(k.ncg) * k.N * 16;
+    for (const HChunk& ch : k.chunks) total += size_t(k.phases) * ch.taps.size() * size_t(k.ncg) * k.N * 16;
   }
   std::vector<T> host(total / sizeof(T), to_t<T>(0.f));
   for (HConv& k : c->convs) {
     size_t off = k.w_off;
+    for (int ph = 0; ph < k.phases; ++ph)
     for (const HChunk& ch : k.chunks) {
       const std::vector<float>* w = find_w(c, ch.wname);
       if (!w) return fail(c, FDSR_E_NOTFOUND, "missing weight %s", ch.wname.c_str());
@@ -512,8 +527,19 @@ int pack_weights(fdsr_ctx* c) {
             for (int j = 0; j < 8; ++j) {
               const int ci = cg * 8 + j;
               if (ci >= ch.creal) continue;
-              const size_t wi = ((size_t(k.w_n0 + n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk +
-                                (is1x1 ? 0 : tp.kx);
+              const size_t wbase = (size_t(k.w_n0 + n) * cin_w + ch.wc0 + ci) * kk * kk;
+              if (k.phases == 4) {
+                // tap (ry, rx) of phase (py, px): the 3x3 taps whose upsampled source row / column is that one
+                const int py = ph >> 1, px = ph & 1;
+                float acc = 0.f;
+                for (int dy = 0; dy < 3; ++dy)
+                  for (int dx = 0; dx < 3; ++dx)
+                    if (((py + dy + 1) >> 1) - py == tp.ky && ((px + dx + 1) >> 1) - px == tp.kx)
+                      acc += (*w)[wbase + dy * 3 + dx];
+                blob[(size_t(cg) * k.N + n) * 8 + j] = to_t<T>(acc);
+                continue;
+              }
+              const size_t wi = wbase + (is1x1 ? 0 : tp.ky) * kk + (is1x1 ? 0 : tp.kx);
               blob[(size_t(cg) * k.N + n) * 8 + j] = to_t<T>((*w)[wi]);
             }
         off += size_t(k.ncg) * k.N * 16;
@@ -718,6 +744,22 @@ bool make_out_map(CUtensorMap* m, void* ptr, int B, int H, int W, int C, bool bf
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Output of a phase-decomposed upsample conv: parity (py, px) = (ph >> 1, ph & 1) of the NHWC 16-bit tensor
+// [B][2h][2w][C] viewed as a rank-4 tensor {C, w, h, B} over the low-resolution grid
+bool make_out_map_phase(CUtensorMap* m, void* ptr, int B, int h, int w, int C, int ph, bool bf16) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const int Wo = 2 * w, Ho = 2 * h;
+  uint8_t* base = static_cast<uint8_t*>(ptr) + (size_t(ph >> 1) * Wo + (ph & 1)) * C * 2;
+  const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(w), cuuint64_t(h), cuuint64_t(B)};
+  const cuuint64_t strides[3] = {cuuint64_t(C) * 4, cuuint64_t(Wo) * C * 4, cuuint64_t(Ho) * Wo * C * 2};
+  const cuuint32_t box[4] = {32, cuuint32_t(kTileW), 4, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // NHWC 16-bit source [B][H][W][C] as a rank-4 TMA tensor {C, W, H, B}, box {64 ch, 10, 34, 1}, 128B swizzle:
 // one load = one 64-channel input patch with halo, pixel-major 128-byte rows, zero-filled outside the image
 bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16, bool center) {
@@ -884,11 +926,13 @@ int upload_layers(fdsr_ctx* c) {
     memset(&l, 0, sizeof l);
     const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
     l.B = B;
-    l.H = H >> lvl;
-    l.W = W >> lvl;
+    l.phases = k.phases;
+    // a phase layer tiles the low-resolution grid once per output parity (virtual images = B * 4)
+    l.H = (H >> lvl) >> (k.phases == 4 ? 1 : 0);
+    l.W = (W >> lvl) >> (k.phases == 4 ? 1 : 0);
     l.tiles_x = (l.W + kTileW - 1) / kTileW;
     l.tiles_y = (l.H + kTileH - 1) / kTileH;
-    l.ntiles = B * l.tiles_x * l.tiles_y;
+    l.ntiles = B * k.phases * l.tiles_x * l.tiles_y;
     // Split-N: a low-resolution layer with fewer 256-pixel tiles than half the SMs is computed as two
     // 128-column halves by twice as many CTAs.  Only 256 -> 2 x 128: both widths use the same
     // per-tile statistics path, so results stay bitwise independent of the batch size.
@@ -952,9 +996,15 @@ int upload_layers(fdsr_ctx* c) {
     if (k.out_mode == kOutAct) {
       const HTensor& t = c->tensors[k.out];
       l.out = c->d_ws + t.off;
-      l.use_tma_store = (c->tma_store && k.N >= 32 &&
-                         make_out_map(&l.out_map, l.out, B, l.H, l.W, k.N, c->cfg.dtype == FDSR_DTYPE_BF16))
-                            ? 1 : 0;
+      const bool bf = c->cfg.dtype == FDSR_DTYPE_BF16;
+      if (k.phases == 4) {
+        bool ok = l.a_tma != 0;
+        for (int ph = 0; ph < 4 && ok; ++ph)
+          ok = make_out_map_phase(ph == 0 ? &l.out_map : &l.out_map_ph[ph - 1], l.out, B, l.H, l.W, k.N, ph, bf);
+        if (!ok) return fail(c, FDSR_E_CUDA, "layer %s: tensor maps of the phase-decomposed upsample conv failed", k.name.c_str());
+        l.use_tma_store = 1;
+      } else
+      l.use_tma_store = (c->tma_store && k.N >= 32 && make_out_map(&l.out_map, l.out, B, l.H, l.W, k.N, bf)) ? 1 : 0;
       l.out_stats = t.stats ? reinterpret_cast<unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
       int su = 1;
       while (su < 8 && t.unit % (4 * su) == 0) su *= 2;  // largest power of two with 2*su | unit, <= 8 pairs
@@ -1044,9 +1094,7 @@ int launch_conv(fdsr_ctx* c, int li, int t, cudaStream_t st) {
 template <typename T>
 int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st) {
   const HConv& k = c->convs[li];
-  const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
-  const int h = c->H >> lvl, w = c->W >> lvl;
-  const int ntiles = c->B * ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH);
+  const int ntiles = c->h_layers[li].ntiles;
   switch (c->h_layers[li].N) {
     case 16: return launch_conv_t<16, T>(c, li, ntiles, t, st);
     case 64: return launch_conv_t<64, T>(c, li, ntiles, t, st);
@@ -1315,6 +1363,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tma_in = !(e6 && e6[0] == '0');
     const char* e7 = getenv("FDSR_TWO_RINGS");
     c->two_rings = !(e7 && e7[0] == '0');
+    const char* e9 = getenv("FDSR_UP_PHASES");
+    c->up_phases = !(e9 && e9[0] == '0');
     const char* e8 = getenv("FDSR_ATTN_REF");
     c->attn_ref = e8 && e8[0] == '1';
   }
@@ -1759,7 +1809,7 @@ double fdsr_debug_op_flops(const fdsr_ctx* c, int32_t i) {
   const HConv& k = c->convs[c->ops[i].idx];
   const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
   double macs = 0.0;
-  for (const HChunk& ch : k.chunks) macs += double(ch.taps.size()) * ch.creal;
+  for (const HChunk& ch : k.chunks) macs += double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
   return 2.0 * macs * k.cout * double(c->B) * (c->H >> lvl) * (c->W >> lvl);
 }
 

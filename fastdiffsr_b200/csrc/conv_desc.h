@@ -72,6 +72,10 @@ struct ConvLayer {
   // out-of-image positions zero-filled (valid when a_tma = 1)
   CUtensorMap in_map[kMaxSrc];
   CUtensorMap in_map_c[kMaxSrc];  // same tensors, box {64 ch, 8, 32, 1}: centre-only chunks (1x1 residual conv)
+  // phases = 4 (nearest-x2 upsample + 3x3 conv evaluated as four 2x2 convs on the low-resolution input, one per
+  // output parity (py, px)): strided views of the output tensor for phases 1..3 (phase 0 uses out_map): dims
+  // {C, W, H, B} of the low-resolution grid, element strides {1, 2C, 2*Wout*C, Hout*Wout*C}, base + (py*Wout + px)*C
+  CUtensorMap out_map_ph[3];
   ConvSrc src[kMaxSrc];
   ConvChunk chunk[kMaxChunks];
   int32_t nchunks;
@@ -102,6 +106,8 @@ struct ConvLayer {
   int32_t out_mode;     // OutMode
   int32_t out_c;
   const uint8_t* weights;  // packed blobs
+  int32_t phases;          // 1, or 4: tiles run over virtual images (image * 4 + phase), H/W are the low-resolution
+                           // grid, every tap position is shifted by (py*kPatchW + px), weights are per phase
   int32_t tiles_x, tiles_y, ntiles;
   int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)
   int32_t dbg;             // experiments (tools/): bit0 skip epilogue work, bit1 skip producer work

@@ -379,12 +379,17 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // tile, tile after tile), so a stage may end in the middle of a chunk and a chunk in the middle of a
     // stage: bq = taps of the current stage already consumed.
     int bq = 0;
+    // phase layers (L.phases = 4): tiles run over virtual images bv = image * 4 + (py * 2 + px); the 2x2 taps of
+    // phase (py, px) are the phase-0 taps shifted by (py, px) positions inside the low-resolution patch
+    int m_bv = tile_begin / tiles_per_img, m_tin = tile_begin - m_bv * tiles_per_img;
     PROF_DECL;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(bar_acc_empty(acc), accph ^ 1);
       PROF_MARK(0);
       tc_fence_after();
       const uint32_t d0 = tmem + acc * Cfg::kAccCols;
+      const uint32_t phoff = L.phases > 1 ? uint32_t(((m_bv >> 1) & 1) * kPatchW + (m_bv & 1)) << pos_sh : 0u;
+      if (++m_tin == tiles_per_img) { m_tin = 0; ++m_bv; }
       for (int c = 0; c < L.nchunks; ++c) {
         const ConvChunk& ck = L.chunk[c];
         const int ntaps = ck.ntaps;
@@ -406,7 +411,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (elect_one()) {
             uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4) + bq * (blob >> 4);
             for (int tg = 0; tg < g; ++tg, b_lo += blob >> 4) {
-              const uint32_t a_lo = a_stage + (cen ? 0u : uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh);
+              const uint32_t a_lo = a_stage + (cen ? 0u : (uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh) + phoff);
               const uint32_t accum0 = (c | tp0 | tg) == 0 ? 0u : 1u;
               if (ksteps == 4) {
 #pragma unroll
@@ -481,6 +486,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     int b_q = 0, b_qq = 0, bs = 0, bph = 0;  // next tap overall / inside its tile
     const uint8_t* const w0 = L.weights + size_t(n_off) * 16;
     int b_issued = 0;
+    // phase layers: the weights of phase p follow those of phase p-1 (taps_tile blobs each); w_bv / w_tin = virtual
+    // image / tile-in-image of the tile that tap b_q belongs to
+    const int phsh = L.phases > 1 ? 2 : 0;
+    const size_t ph_stride = L.phases > 1 ? size_t(taps_tile) * gblob : 0;
+    int w_bv = tile_begin / tiles_per_img, w_tin = tile_begin - w_bv * tiles_per_img;
     while (a_next < total || b_q < total_taps) {
       bool progress = false;
       if (!dep_ok && (b_issued >= Cfg::kBStages || b_q >= total_taps)) {
@@ -497,16 +507,16 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             const uint32_t dst = sA + slot_off(a_as);
             if (ak.gn != 0) {
               mbar_arrive_expect_tx(bar_raw_full(a_as), kPatchBytesSw);
-              tma_load_4d(&L.in_map[ak.src], dst, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
+              tma_load_4d(&L.in_map[ak.src], dst, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b >> phsh);
             } else {
               const uint32_t bar = bar_a_full(a_as);
               mbar_arrive_cnt(bar, kProdWarps - 1);  // stands in for the producer warps
               if (ak.center != 0) {
                 mbar_arrive_expect_tx(bar, kTileH * kTileW * 128);
-                tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, a_tx * kTileW, a_ty * kTileH, a_b);
+                tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, a_tx * kTileW, a_ty * kTileH, a_b >> phsh);
               } else {
                 mbar_arrive_expect_tx(bar, kPatchBytesSw);
-                tma_load_4d(&L.in_map[ak.src], dst, bar, ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
+                tma_load_4d(&L.in_map[ak.src], dst, bar, ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b >> phsh);
               }
             }
           }
@@ -535,13 +545,24 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             mbar_arrive_expect_tx(bar_b_full(bs), uint32_t(g) * blob);  // own slices + the peers' multicast slices
             const uint32_t dst0 = sB + bs * Cfg::kBStageBytes;
             if (csize == 1 && nsplit == 1) {
-              const int first = g < taps_tile - b_qq ? g : taps_tile - b_qq;  // up to the end of the tile's taps
-              bulk_g2s(dst0, w0 + size_t(b_qq) * blob, uint32_t(first) * blob, bar_b_full(bs));
-              if (first < g) bulk_g2s(dst0 + uint32_t(first) * blob, w0, uint32_t(g - first) * blob, bar_b_full(bs));
+              // contiguous runs up to the end of each tile's taps (the next tile may belong to another phase)
+              int rem = g, qq = b_qq, tin = w_tin, bv = w_bv;
+              uint32_t dst = dst0;
+              while (rem > 0) {
+                const int n = rem < taps_tile - qq ? rem : taps_tile - qq;
+                bulk_g2s(dst, w0 + size_t(bv & 3) * ph_stride + size_t(qq) * blob, uint32_t(n) * blob, bar_b_full(bs));
+                dst += uint32_t(n) * blob;
+                rem -= n;
+                qq += n;
+                if (qq == taps_tile) {
+                  qq = 0;
+                  if (++tin == tiles_per_img) { tin = 0; ++bv; }
+                }
+              }
             } else {
-              int qq = b_qq;
+              int qq = b_qq, tin = w_tin, bv = w_bv;
               for (int tg = 0; tg < g; ++tg) {
-                const uint8_t* wt = w0 + size_t(qq) * gblob;
+                const uint8_t* wt = w0 + size_t(bv & 3) * ph_stride + size_t(qq) * gblob;
                 const uint32_t dst = dst0 + uint32_t(tg) * blob;
                 if (csize > 1) {
                   const uint32_t slice = blob / csize;
@@ -551,14 +572,18 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                   for (int cgi = 0; cgi < ncg; ++cgi)
                     bulk_g2s(dst + uint32_t(cgi) * N * 16, wt + size_t(cgi) * n_full * 16, N * 16, bar_b_full(bs));
                 }
-                if (++qq == taps_tile) qq = 0;
+                if (++qq == taps_tile) {
+                  qq = 0;
+                  if (++tin == tiles_per_img) { tin = 0; ++bv; }
+                }
               }
             }
           }
           __syncwarp();
           if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
           b_q += g;
-          b_qq = (b_qq + g) % taps_tile;
+          for (b_qq += g; b_qq >= taps_tile; b_qq -= taps_tile)
+            if (++w_tin == tiles_per_img) { w_tin = 0; ++w_bv; }
           ++b_issued;
           progress = true;
         }
@@ -601,7 +626,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       const int x = tx * kTileW + r, y = ty * kTileH + mt * 16 + g;
       const bool valid = y < H && x < W;
       const bool all_valid = __all_sync(0xffffffffu, valid);
-      const uint32_t pix = uint32_t((b * H + y) * W + x);  // < 2^31 pixels per tensor
+      // phase layers: b is a virtual image (image * 4 + py * 2 + px) and (y, x) a low-resolution position whose output
+      // pixel is (2y + py, 2x + px) of the 2H x 2W tensor
+      const int ph = L.phases > 1 ? (b & 3) : 0, b_img = L.phases > 1 ? (b >> 2) : b;
+      const uint32_t pix = L.phases > 1 ? uint32_t((b_img * 2 * H + 2 * y + (ph >> 1)) * 2 * W + 2 * x + (ph & 1))
+                                        : uint32_t((b * H + y) * W + x);  // < 2^31 pixels per tensor
       const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(L.resid) +
                                                        (size_t(pix) * n_full + n_off) * 2);
       uint8_t* const orow = reinterpret_cast<uint8_t*>(L.out) + (size_t(pix) * n_full + n_off) * 2;
@@ -676,7 +705,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_4d(&L.out_map, stage_s, n_off + cb * 32, tx * kTileW, ty * kTileH + mt * 16 + q * 4, b);
+              tma_store_4d(ph == 0 ? &L.out_map : &L.out_map_ph[ph - 1], stage_s, n_off + cb * 32, tx * kTileW,
+                           ty * kTileH + mt * 16 + q * 4, b_img);
               bulk_commit_group();
             }
           } else if (valid && !(L.dbg & 4)) {
@@ -781,7 +811,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       PROF_MARK(1);
       if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
       // next tile coordinates (no divisions in the loop)
-      const int b_cur = b;
+      const int b_cur = b_img;
       if (++tx == tiles_x) {
         tx = 0;
         if (++ty == L.tiles_y) { ty = 0; ++b; }
