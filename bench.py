@@ -239,6 +239,11 @@ def run_ours(args, rank, world, local_rank):
                 "timing": "CUDA events around each of the 52 conv launches, mean of the last 12 of 24 back-to-back UNet "
                           "evaluations at the benchmark shape (sustained clocks)",
                 "other_ms_per_unet_step": sum(ms for _, ms, fl in prof if fl == 0),
+                "flop_accounting": "algorithmic FLOPs (2*MAC of the reference's convs, zero padding counted: 268.31 GFLOP "
+                                   "per 256^2 image per UNet step, SURVEY 8(d)); the three nearest-upsample convs are "
+                                   "executed as four 2x2 phase convs on the low-resolution input (an exact identity, "
+                                   "4/9 of their MACs: 244.15 GFLOP per image per step executed) and are accounted at their "
+                                   "algorithmic nine-tap cost; FDSR_UP_PHASES=0 runs the nine-tap form",
                 "whole_step_frac": value / world * flop_per_image / 1e12 / peak}
 
     cpu = None

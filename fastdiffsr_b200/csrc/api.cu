@@ -108,6 +108,9 @@ struct fdsr_ctx {
   std::vector<F32Layer> f_layers;   // fp32 parity mode: the same plan for conv_f32_kernel
   std::vector<F32GnArgs> f_gn;
   std::vector<AttnParams> a_params;  // per HAttn of kind 1 (16-bit modes)
+  bool split_all = false;            // FDSR_SPLIT_ALL=1: every 256-wide layer runs as two 128-column halves (experiment)
+  bool s2d_tma = true;               // FDSR_S2D_TMA=0: stride-2 convs gather their parity planes with the producer warps
+  bool resid_mma = true;             // FDSR_RESID_MMA=0: identity residuals are always added by the epilogue
   bool up_phases = true;             // FDSR_UP_PHASES=0: nearest-upsample convs gather a 2x patch and run all nine taps
   bool attn_ref = false;             // FDSR_ATTN_REF=1: CUDA-core attention core in the 16-bit modes too
   float* d_weights32 = nullptr;     // fp32 parity mode weights: per conv, per chunk [tap][ci][N]
@@ -242,6 +245,14 @@ int add_res(fdsr_ctx* c, const std::string& name, const std::vector<int>& srcs, 
         ++k.nsrc;
       }
       k.bias_names.push_back(p + ".res_conv.bias");
+    } else if (c->resid_mma && c->cfg.dtype != FDSR_DTYPE_FP32 && pad_n(cout) == 64) {
+      // identity residual of an N = 64 layer as one more K chunk with the identity matrix as weights: x * 1 is exact
+      // in fp16/bf16 and accumulates in fp32 like the epilogue's add, but the tile arrives by TMA (centre box) and
+      // the epilogue — the bottleneck of these layers — neither loads nor adds it (8 extra MMAs per 72)
+      k.src[k.nsrc] = srcs[0];
+      for (int c0 = 0; c0 < cout; c0 += 64)
+        k.chunks.push_back({k.nsrc, c0, 0, 0, -1, {{0, 0, kPatchW + 1}}, "@identity", c0, 64, 1});
+      ++k.nsrc;
     } else {
       k.resid = srcs[0];
     }
@@ -483,7 +494,7 @@ int build_plan(fdsr_ctx* c) {
     if (k.gn_C > kMaxGnC) return fail(c, FDSR_E_INVALID, "layer %s: GroupNorm width %d > %d", k.name.c_str(), k.gn_C, kMaxGnC);
     const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
     double macs = 0.0;  // algorithmic: a phase layer is accounted as the nine-tap conv it replaces
-    for (const HChunk& ch : k.chunks) macs += double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
+    for (const HChunk& ch : k.chunks) macs += ch.wname == "@identity" ? 0.0 : double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
     fl += 2.0 * macs * k.cout / double(1 << (2 * lvl));
   }
   c->flops_per_px = fl;
@@ -491,6 +502,14 @@ int build_plan(fdsr_ctx* c) {
 }
 
 const std::vector<float>* find_w(fdsr_ctx* c, const std::string& name) {
+  if (name == "@identity") {  // 256 x 256 identity (1x1 "weights" of an identity-residual K chunk)
+    static const std::vector<float> eye = [] {
+      std::vector<float> e(256 * 256, 0.f);
+      for (int i = 0; i < 256; ++i) e[i * 256 + i] = 1.f;
+      return e;
+    }();
+    return &eye;
+  }
   auto it = c->host_w.find(name);
   return it == c->host_w.end() ? nullptr : &it->second;
 }
@@ -519,7 +538,7 @@ int pack_weights(fdsr_ctx* c) {
       if (!w) return fail(c, FDSR_E_NOTFOUND, "missing weight %s", ch.wname.c_str());
       const bool is1x1 = ch.kk == 1;
       const int kk = ch.kk;
-      const size_t cin_w = w->size() / (size_t(k.w_rows ? k.w_rows : k.cout) * kk * kk);
+      const size_t cin_w = ch.wname == "@identity" ? 256 : w->size() / (size_t(k.w_rows ? k.w_rows : k.cout) * kk * kk);
       for (const HTap& tp : ch.taps) {
         T* blob = host.data() + off / sizeof(T);
         for (int cg = 0; cg < k.ncg; ++cg)
@@ -571,7 +590,7 @@ int pack_weights_f32(fdsr_ctx* c) {
       if (!w) return fail(c, FDSR_E_NOTFOUND, "missing weight %s", ch.wname.c_str());
       const bool is1x1 = ch.kk == 1;
       const int kk = ch.kk;
-      const size_t cin_w = w->size() / (size_t(k.w_rows ? k.w_rows : k.cout) * kk * kk);
+      const size_t cin_w = ch.wname == "@identity" ? 256 : w->size() / (size_t(k.w_rows ? k.w_rows : k.cout) * kk * kk);
       for (const HTap& tp : ch.taps) {
         for (int ci = 0; ci < ch.creal; ++ci)
           for (int n = 0; n < k.cout; ++n)
@@ -762,13 +781,16 @@ bool make_out_map_phase(CUtensorMap* m, void* ptr, int B, int h, int w, int C, i
 
 // NHWC 16-bit source [B][H][W][C] as a rank-4 TMA tensor {C, W, H, B}, box {64 ch, 10, 34, 1}, 128B swizzle:
 // one load = one 64-channel input patch with halo, pixel-major 128-byte rows, zero-filled outside the image
-bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16, bool center) {
+// kind 0: full patch; 1: centre box {64, 8, 32}; 2: space-to-depth plane = box {64, 20, 68} traversed with element
+// strides {1, 2, 2, 1} (every second pixel in x and y: 10 x 34 positions land in shared memory)
+bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16, int kind) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc || C < 64) return false;
   const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
   const cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
-  const cuuint32_t box[4] = {64, cuuint32_t(center ? kTileW : kPatchW), cuuint32_t(center ? kTileH : kPatchH), 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint32_t sc = kind == 2 ? 2 : 1;
+  const cuuint32_t box[4] = {64, cuuint32_t(kind == 1 ? kTileW : kPatchW) * sc, cuuint32_t(kind == 1 ? kTileH : kPatchH) * sc, 1};
+  const cuuint32_t estr[4] = {1, sc, sc, 1};
   return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -936,7 +958,8 @@ int upload_layers(fdsr_ctx* c) {
     // Split-N: a low-resolution layer with fewer 256-pixel tiles than half the SMs is computed as two
     // 128-column halves by twice as many CTAs.  Only 256 -> 2 x 128: both widths use the same
     // per-tile statistics path, so results stay bitwise independent of the batch size.
-    l.nsplit = (c->split_n && k.out_mode == kOutAct && k.N == 256 && !c->cluster2 && 2 * l.ntiles <= c->num_sms) ? 2 : 1;
+    l.nsplit = (c->split_n && k.out_mode == kOutAct && k.N == 256 && !c->cluster2 &&
+                (2 * l.ntiles <= c->num_sms || c->split_all)) ? 2 : 1;
     l.n_full = k.N;
     l.N = k.N / l.nsplit;
     l.ncg = k.ncg;
@@ -949,12 +972,13 @@ int upload_layers(fdsr_ctx* c) {
       l.src[s].H = H >> t.level;
       l.src[s].W = W >> t.level;
     }
-    l.a_tma = (c->tma_in && k.mode == kModeNormal && k.ncg == 8) ? 1 : 0;
+    const bool s2d_tma = k.mode == kModeS2D && c->s2d_tma;
+    l.a_tma = (c->tma_in && (k.mode == kModeNormal || s2d_tma) && k.ncg == 8) ? 1 : 0;
     for (int s = 0; s < k.nsrc && l.a_tma; ++s)
       if (!make_in_map(&l.in_map[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
-                       c->cfg.dtype == FDSR_DTYPE_BF16, false) ||
+                       c->cfg.dtype == FDSR_DTYPE_BF16, 0) ||
           !make_in_map(&l.in_map_c[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
-                       c->cfg.dtype == FDSR_DTYPE_BF16, true))
+                       c->cfg.dtype == FDSR_DTYPE_BF16, s2d_tma ? 2 : 1))
         l.a_tma = 0;
     l.nchunks = int(k.chunks.size());
     int any_center = 0;
@@ -970,7 +994,8 @@ int upload_layers(fdsr_ctx* c) {
       d.ntaps = int(ch.taps.size());
       d.w_off = int(woff);
       for (int tp = 0; tp < d.ntaps; ++tp) d.tap_pos[tp] = ch.taps[tp].pos;
-      d.center = (l.a_tma && ch.gn == 0 && d.ntaps == 1 && d.tap_pos[0] == kPatchW + 1) ? 1 : 0;
+      d.parity = ch.parity < 0 ? 0 : ch.parity;
+      d.center = (l.a_tma && k.mode == kModeNormal && ch.gn == 0 && d.ntaps == 1 && d.tap_pos[0] == kPatchW + 1) ? 1 : 0;
       any_center += d.center;
       woff += ch.taps.size() * size_t(k.ncg) * k.N * 16;
     }
@@ -1061,7 +1086,10 @@ int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
   const int cs = (c->cluster2 && ngroups % 2 == 0 && ngroups >= 2) ? 2 : 1;
   int grid = ngroups < c->num_sms ? ngroups : c->num_sms;
   grid -= grid % cs;
-  if (nsplit > 1) grid = ngroups * nsplit;  // nsplit CTAs per tile group (chosen so that this fits one wave)
+  if (nsplit > 1) {  // nsplit CTAs per tile group; persistent over the groups when there are more than fit one wave
+    grid = ngroups * nsplit;
+    if (grid > c->num_sms) grid = c->num_sms - c->num_sms % nsplit;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads);
@@ -1363,6 +1391,12 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tma_in = !(e6 && e6[0] == '0');
     const char* e7 = getenv("FDSR_TWO_RINGS");
     c->two_rings = !(e7 && e7[0] == '0');
+    const char* e12 = getenv("FDSR_SPLIT_ALL");
+    c->split_all = e12 && e12[0] == '1';
+    const char* e11 = getenv("FDSR_S2D_TMA");
+    c->s2d_tma = !(e11 && e11[0] == '0');
+    const char* e10 = getenv("FDSR_RESID_MMA");
+    c->resid_mma = !(e10 && e10[0] == '0');
     const char* e9 = getenv("FDSR_UP_PHASES");
     c->up_phases = !(e9 && e9[0] == '0');
     const char* e8 = getenv("FDSR_ATTN_REF");
@@ -1809,7 +1843,7 @@ double fdsr_debug_op_flops(const fdsr_ctx* c, int32_t i) {
   const HConv& k = c->convs[c->ops[i].idx];
   const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
   double macs = 0.0;
-  for (const HChunk& ch : k.chunks) macs += double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
+  for (const HChunk& ch : k.chunks) macs += ch.wname == "@identity" ? 0.0 : double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
   return 2.0 * macs * k.cout * double(c->B) * (c->H >> lvl) * (c->W >> lvl);
 }
 

@@ -53,6 +53,7 @@ struct ConvChunk {
   int32_t ring;       // patch ring of this chunk: 0 = full stages, 1 = 32 KB centre-box stages (ConvLayer::nR > 0)
   int32_t center;     // 1: TMA-fed raw chunk whose only tap is the centre one: staged as a dense 32x8 box (no halo)
   int32_t w_off;      // byte offset of this chunk's first tap blob inside the layer's weights
+  int32_t parity;     // kModeS2D: pa*2 + pb of the space-to-depth plane this chunk reads (TMA-fed form), else 0
   int32_t tap_pos[kMaxTaps];  // A-operand position offset of each tap (dy*kPatchW + dx)
 };
 
@@ -71,7 +72,9 @@ struct ConvLayer {
   // 128B swizzle: one bulk tensor load stages a whole (32+2)x(8+2) x 64-channel input patch,
   // out-of-image positions zero-filled (valid when a_tma = 1)
   CUtensorMap in_map[kMaxSrc];
-  CUtensorMap in_map_c[kMaxSrc];  // same tensors, box {64 ch, 8, 32, 1}: centre-only chunks (1x1 residual conv)
+  CUtensorMap in_map_c[kMaxSrc];  // same tensors, box {64 ch, 8, 32, 1}: centre-only chunks (1x1 residual conv);
+                                  // kModeS2D: box {64 ch, 20, 68, 1} traversed with element strides {1, 2, 2, 1}: one
+                                  // load = the 10 x 34 patch of one space-to-depth parity plane of the stride-2 conv
   // phases = 4 (nearest-x2 upsample + 3x3 conv evaluated as four 2x2 convs on the low-resolution input, one per
   // output parity (py, px)): strided views of the output tensor for phases 1..3 (phase 0 uses out_map): dims
   // {C, W, H, B} of the low-resolution grid, element strides {1, 2C, 2*Wout*C, Hout*Wout*C}, base + (py*Wout + px)*C

@@ -511,7 +511,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             } else {
               const uint32_t bar = bar_a_full(a_as);
               mbar_arrive_cnt(bar, kProdWarps - 1);  // stands in for the producer warps
-              if (ak.center != 0) {
+              if (L.mode == kModeS2D) {  // parity plane (pa, pb) of the stride-2 conv's input: every second pixel
+                mbar_arrive_expect_tx(bar, kPatchBytesSw);
+                tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, 2 * (a_tx * kTileW - 1) + (ak.parity & 1),
+                            2 * (a_ty * kTileH - 1) + (ak.parity >> 1), a_b);
+              } else if (ak.center != 0) {
                 mbar_arrive_expect_tx(bar, kTileH * kTileW * 128);
                 tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, a_tx * kTileW, a_ty * kTileH, a_b >> phsh);
               } else {

@@ -43,14 +43,20 @@ if os.path.exists(ll):
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"| `{k}` | {n} | {us:.0f} | {100 * us / tot:.1f}% |")
     conv = sum(us for k, (n, us) in agg.items() if "conv_gemm" in k)
-    lines += ["", f"conv_gemm_kernel share of the step: **{100 * conv / tot:.1f}%** of {tot / 1000:.1f} ms "
-              "(bench.py's CUDA-event split: conv 4.85 ms of 5.16 ms per UNet step = 94.1%)", ""]
+    split = ""
+    bj = os.path.join(rd, "bench_n1.json")
+    if os.path.exists(bj):
+        b = json.load(open(bj))
+        cm, st = b["roofline"]["conv_ms_per_unet_step"], b["config"]["ms_per_unet_step"]
+        split = (f" (bench.py's CUDA-event split, `bench_n1.json`: conv launches {cm:.2f} ms, timed with an event pair around "
+                 f"each launch, against {st:.2f} ms per UNet step of the free-running sampling loop)")
+    lines += ["", f"conv_gemm_kernel share of the step: **{100 * conv / tot:.1f}%** of {tot / 1000:.1f} ms" + split, ""]
 # ---- per-kernel details
 want = ["Duration", "SM Frequency", "Compute (SM) Throughput", "Memory Throughput", "DRAM Throughput", "L2 Hit Rate",
         "Registers Per Thread", "Dynamic Shared Memory Per Block", "Issued Warp Per Scheduler", "Executed Instructions",
         "Warp Cycles Per Issued Instruction", "Achieved Active Warps Per SM"]
 names = {"1": "downs.1.block1 (64->64 3x3, N=64, 256^2)", "41": "ups.9.block2 (N=128, 128^2, GN + 1x1 residual chunks)",
-         "37": "ups.7 (up2x conv 256->256, N=256, 128^2)", "47": "ups.13.block1 (128->64, N=64, 256^2)"}
+         "37": "ups.7 (up2x conv 256->256 as four 2x2 phase convs, N=256, 128^2)", "47": "ups.13.block1 (128->64, N=64, 256^2)"}
 for f in sorted(glob.glob(os.path.join(rd, "conv*_details.csv"))):
     idx = os.path.basename(f).split("_")[0].replace("conv", "")
     rows = list(csv.reader(open(f)))
