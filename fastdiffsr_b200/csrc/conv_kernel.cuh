@@ -873,16 +873,33 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     auto build_table = [&](int bb) {
       named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
       const int cpg = L.gn_C / L.gn_groups;
+      // One global-load latency instead of a dependent chain: thread pv fetches the fixed-point (sum, sum of squares)
+      // of channel pair pv of the virtual concat (<= 256 pairs) into the table's own memory, used as scratch until the
+      // table is written; gamma / beta of this thread's channels are requested at the same time.
+      long long* scratch = reinterpret_cast<long long*>(table);
+      const int npairs = L.gn_C >> 1, p0 = L.src[0].C >> 1;
+      if (pidx < npairs) {
+        const int si = pidx < p0 ? 0 : 1;
+        const int pl = pidx < p0 ? pidx : pidx - p0;
+        const longlong2 st = *reinterpret_cast<const longlong2*>(
+            reinterpret_cast<const long long*>(L.src[si].stats) + (size_t(bb) * (L.src[si].C >> 1) + pl) * 2);
+        scratch[2 * pidx] = st.x;
+        scratch[2 * pidx + 1] = st.y;
+      }
+      float ga[2], be[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = pidx + j * kProdThreads;
+        ga[j] = c < L.gn_C ? L.gamma[c] : 0.f;
+        be[j] = c < L.gn_C ? L.beta[c] : 0.f;
+      }
+      named_bar_sync(1, kProdThreads);
       if (pidx < L.gn_groups) {
-        const int ppg = cpg >> 1, p0 = L.src[0].C >> 1;
+        const int ppg = cpg >> 1;
         long long Si = 0, Qi = 0;
         for (int pv = pidx * ppg; pv < (pidx + 1) * ppg; ++pv) {
-          const int si = pv < p0 ? 0 : 1;
-          const int pl = pv < p0 ? pv : pv - p0;
-          const long long* st = reinterpret_cast<const long long*>(L.src[si].stats) +
-                                (size_t(bb) * (L.src[si].C >> 1) + pl) * 2;
-          Si += st[0];
-          Qi += st[1];
+          Si += scratch[2 * pv];
+          Qi += scratch[2 * pv + 1];
         }
         const double n = double(cpg) * L.src[0].H * L.src[0].W;
         const double mean = double(Si) * (1.0 / kStatScale) / n;
@@ -891,15 +908,19 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         gstat[pidx] = make_float2(float(mean), float(1.0 / sqrt(var + double(L.gn_eps))));
       }
       named_bar_sync(1, kProdThreads);
-      for (int c = pidx; c < L.gn_C; c += kProdThreads) {
-        const float2 gs = gstat[c / cpg];
-        const float sc = L.gamma[c] * gs.y;
-        const float sh = L.beta[c] - gs.x * sc;
-        if (kFast) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
-          table_h[c] = __float2half_rn(0.5f * sc);
-          table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
-        } else {
-          table[c] = make_float2(sc, sh);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = pidx + j * kProdThreads;
+        if (c < L.gn_C) {
+          const float2 gs = gstat[c / cpg];
+          const float sc = ga[j] * gs.y;
+          const float sh = be[j] - gs.x * sc;
+          if (kFast) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
+            table_h[c] = __float2half_rn(0.5f * sc);
+            table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
+          } else {
+            table[c] = make_float2(sc, sh);
+          }
         }
       }
       named_bar_sync(1, kProdThreads);
