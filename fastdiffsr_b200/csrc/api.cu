@@ -436,7 +436,7 @@ int build_plan(fdsr_ctx* c) {
       // fall on the same source pixel are added up front (pack_weights), so each output parity is a 2x2 conv on
       // the low-resolution tensor -- 4 instead of 9 MACs per weight, TMA-fed like every other stride-1 layer.
       // An exact identity up to the rounding of the summed weights; the fp32 parity mode keeps the nine-tap form.
-      k.phases = (c->up_phases && g.dtype != FDSR_DTYPE_FP32 && pre >= 128) ? 4 : 1;
+      k.phases = (c->up_phases && c->tma_in && g.dtype != FDSR_DTYPE_FP32 && pre >= 128) ? 4 : 1;
       k.mode = k.phases == 4 ? kModeNormal : kModeUp2x;
       for (int c0 = 0; c0 < pre; c0 += 64) {
         if (k.phases == 4)
