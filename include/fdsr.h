@@ -10,7 +10,8 @@
  *   - "dev" pointers are CUDA device pointers owned by the caller, valid until the stream work
  *     enqueued by the call has completed; "host" pointers are ordinary host memory
  *   - all image tensors are fp32 NCHW (B,3,H,W), the reference's layout; H and W must be
- *     multiples of 8 (three stride-2 levels, model/fastdiffsr_modules/unet.py:77-83)
+ *     multiples of 2^(n_levels-1): 8 for the FastDiffSR UNet (three stride-2 levels,
+ *     model/fastdiffsr_modules/unet.py:77-83), 32 for the SR3 baseline (five)
  *   - calls are asynchronous with respect to the host (enqueue on `stream` and return) unless
  *     stated; a context is single-owner, not thread-safe, bound to the device that was current
  *     at fdsr_create
