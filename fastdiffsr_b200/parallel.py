@@ -74,4 +74,6 @@ def sharded_super_resolution(netG, cond_global: torch.Tensor, noise_global=None,
             noise = torch.cat([noise, pad], dim=1)
         noise = noise.contiguous()
     sr_local = netG.super_resolution(local, False, noise=noise, seed=seed + rank)
+    if sr_local.dim() == 3:   # SR3 baseline, one image per rank: ret_img[-1] has no batch axis
+        sr_local = sr_local[None]
     return gather_batch(sr_local, cond_global.shape[0], group)
