@@ -204,7 +204,7 @@ def _swish(x):
 def noise_embedding(noise_level, dim):
     """unet.py:22-35 — noise_level (B,1) -> (B,1,dim)."""
     count = dim // 2
-    step = torch.arange(count, dtype=noise_level.dtype) / count
+    step = torch.arange(count, dtype=noise_level.dtype, device=noise_level.device) / count
     enc = noise_level.unsqueeze(1) * torch.exp(-math.log(1e4) * step.unsqueeze(0))
     return torch.cat([torch.sin(enc), torch.cos(enc)], dim=-1)
 
@@ -307,7 +307,8 @@ def p_sample_step(sd, cfg, tables, x, t, cond, z, eps=None):
     ``eps`` may be supplied to bypass the UNet (used to test the posterior arithmetic alone)."""
     B = x.shape[0]
     if eps is None:
-        nl = torch.full((B, 1), float(np.float32(tables["sqrt_alphas_cumprod_prev"][t + 1])), dtype=torch.float32)
+        nl = torch.full((B, 1), float(np.float32(tables["sqrt_alphas_cumprod_prev"][t + 1])), dtype=torch.float32,
+                        device=x.device)
         eps = unet_forward(sd, cfg, torch.cat([cond, x], dim=1), nl)
     x0 = _f32(tables, "sqrt_recip_alphas_cumprod", t) * x - _f32(tables, "sqrt_recipm1_alphas_cumprod", t) * eps
     x0 = x0.clamp(-1.0, 1.0)
