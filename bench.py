@@ -184,8 +184,10 @@ def run_ours(args, rank, world, local_rank):
         acc.add_(local)
         return sr
 
+    sr_host = np.zeros((B, 3, H, H), dtype=np.float32)   # caller-owned result buffer, reused every step
+
     def step_host(i):
-        return eng.super_resolve_u8_host(lr_host, H, H, seed=2000 + i)
+        return eng.super_resolve_u8_host(lr_host, H, H, seed=2000 + i, out=sr_host)
 
     def sync():
         torch.cuda.synchronize(dev)

@@ -152,11 +152,15 @@ class Engine:
                                                  self._stream()), "fdsr_bicubic_u8")
         return o8, oc
 
-    def super_resolve_u8_host(self, lr_host: np.ndarray, H: int, W: int, noise=None, seed: int = 0):
-        """Host uint8 (B,h,w,3) -> host fp32 (B,3,H,W): H2D, bicubic, T-step sampling, D2H."""
+    def super_resolve_u8_host(self, lr_host: np.ndarray, H: int, W: int, noise=None, seed: int = 0, out=None):
+        """Host uint8 (B,h,w,3) -> host fp32 (B,3,H,W): H2D, bicubic, T-step sampling, D2H.
+        `out`: optional caller-owned C-contiguous float32 (B,3,H,W) array to fill (avoids a fresh allocation per call)."""
         lr_host = np.ascontiguousarray(lr_host, dtype=np.uint8)
         B, h, w, _ = lr_host.shape
-        out = np.empty((B, 3, H, W), dtype=np.float32)
+        if out is None:
+            out = np.empty((B, 3, H, W), dtype=np.float32)
+        elif out.shape != (B, 3, H, W) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise FdsrError(f"out must be a C-contiguous float32 array of shape {(B, 3, H, W)}")
         with torch.cuda.device(self.device):
             self._check(self.lib.fdsr_super_resolve_u8(self._h, lr_host.ctypes.data_as(C.c_void_p), B, h, w, H, W,
                                                        _ptr(noise), seed, out.ctypes.data_as(C.c_void_p),
