@@ -142,3 +142,20 @@ def test_cabi_library_exports_every_declared_symbol():
         l = _lib.load()
         assert l.fdsr_create(ctypes.byref(cfg), ctypes.byref(h)) < 0
         assert b"no CPU fallback" in l.fdsr_global_error() or b"CUDA" in l.fdsr_global_error()
+
+
+def test_cabi_from_plain_c(tmp_path):
+    """include/fdsr.h compiles as C and links against libfdsr.so from a C program (no C++ / torch types at the
+    boundary); without a GPU fdsr_create reports FDSR_E_CUDA instead of falling back."""
+    import shutil
+    import subprocess
+    from fastdiffsr_b200._lib import LIB_PATH
+    if shutil.which("gcc") is None or not os.path.exists(LIB_PATH):
+        pytest.skip("gcc or libfdsr.so missing")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_check")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c_abi", "abi_check.c"), "-o", exe, LIB_PATH,
+                    "-Wl,-rpath," + os.path.dirname(LIB_PATH)], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
