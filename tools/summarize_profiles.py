@@ -51,6 +51,33 @@ if os.path.exists(ll):
         split = (f" (bench.py's CUDA-event split, `bench_n1.json`: conv launches {cm:.2f} ms, timed with an event pair around "
                  f"each launch, against {st:.2f} ms per UNet step of the free-running sampling loop)")
     lines += ["", f"conv_gemm_kernel share of the step: **{100 * conv / tot:.1f}%** of {tot / 1000:.1f} ms" + split, ""]
+    # ---- HBM-bound helper kernels: algorithmic bytes per launch (B = 16, 256^2) / mean duration in the launch list
+    px = 16 * 256 * 256
+    algo = {  # kernel -> (bytes per launch, what)
+        "pack_input_kernel<__half>": (px * (6 * 4 + 16 * 2), "reads cond + x_t fp32 NCHW, writes 16-channel NHWC fp16"),
+        "posterior_kernel": (px * 3 * 4 * 3, "reads x_t, eps, writes x_{t-1} (fp32; z from Philox in-kernel)"),
+        "res2img_kernel": (px * 3 * 4 * 3, "reads x_0, cond, writes SR (fp32)"),
+        "noise_fill_kernel": (px * 3 * 4, "writes x_T (Philox normals)"),
+        "slam_apply_kernel<__half>": (16 * 32 * 32 * 256 * 2 * 2, "reads + writes the (B,32,32,256) mid tensor"),
+        "bicubic_v_kernel": (16 * (64 * 256 * 3 + 256 * 256 * 3 * 4), "reads the horizontally resampled u8 rows, writes cond fp32"),
+    }
+    peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    hbm = None
+    if os.path.exists(peaks):
+        pk = json.load(open(peaks))
+        hbm = pk.get("hbm_gbs")
+    lines += ["## Elementwise / norm helper kernels: achieved HBM bandwidth (algorithmic bytes / mean launch duration from the list above; "
+              "12-60 MB per launch, so launch latency is a visible part of each figure)", "",
+              "| kernel | MB per launch | mean us | GB/s | traffic |", "|---|---:|---:|---:|---|"]
+    for k, (nbytes, what) in algo.items():
+        if k in agg and agg[k][0] > 0:
+            us = agg[k][1] / agg[k][0]
+            lines.append(f"| `{k}` | {nbytes / 1e6:.1f} | {us:.1f} | {nbytes / us / 1e3:.0f} | {what} |")
+    if hbm:
+        lines += ["", f"(measured HBM copy bandwidth of this pool, MEASURED_PEAKS.json: {hbm:.0f} GB/s; these kernels are "
+                  "0.6 % of the step)", ""]
+    else:
+        lines.append("")
 # ---- per-kernel details
 want = ["Duration", "SM Frequency", "Compute (SM) Throughput", "Memory Throughput", "DRAM Throughput", "L2 Hit Rate",
         "Registers Per Thread", "Dynamic Shared Memory Per Block", "Issued Warp Per Scheduler", "Executed Instructions",
