@@ -30,6 +30,13 @@ class FdsrError(RuntimeError):
     pass
 
 
+class FdsrOverflowError(FdsrError, FloatingPointError):
+    """fp16 mode: an activation left the fp16 range during the call (FDSR_E_OVERFLOW)."""
+
+
+E_OVERFLOW = -5
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile libfdsr.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
@@ -82,6 +89,11 @@ _SIGS = {
                                           C.c_void_p]),
     "fdsr_debug_role_cycles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int32,
                                          C.c_void_p]),
+    "fdsr_check_overflow": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fdsr_set_image_offset": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "fdsr_debug_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64,
+                                   C.c_int32, C.c_void_p]),
+    "fdsr_graph_captures": (C.c_int64, [C.c_void_p]),
     "fdsr_launch_count": (C.c_int64, [C.c_void_p]),
     "fdsr_unet_flops": (C.c_double, [C.c_void_p]),
     "fdsr_set_use_graph": (C.c_int, [C.c_void_p, C.c_int32]),

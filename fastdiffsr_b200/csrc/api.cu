@@ -1,6 +1,7 @@
 // libfdsr: C-ABI, context, layer plan, weight packing and launch orchestration (see include/fdsr.h).
 // The plan mirrors UNet.__init__/forward of the reference (model/fastdiffsr_modules/unet.py:224-323);
 // each ResnetBlock becomes two conv_gemm_kernel launches, each Down/Upsample one.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -58,6 +59,8 @@ struct HConv {
   bool film_swish = false;   // FiLM vector = Linear(swish(emb)) (SR3 ResnetBlock.mlp) instead of Linear(emb)
   // device-side resources
   size_t w_off = 0;      // into weight arena
+  size_t w_off2 = 0, w_bytes = 0;  // pair-capable layers: a second copy as two half-width layouts (CTA pairs), layer bytes
+  bool pair_ok() const { return ncg == 8 && N >= 64 && out_mode == kOutAct; }
   size_t gamma_off = 0;  // into param arena (floats)
   size_t bias_off = 0;   // into bias arena (floats), [T][N]
 };
@@ -142,13 +145,26 @@ struct fdsr_ctx {
   bool tma_in = true;    // FDSR_TMA_IN=0: producer warps gather every input patch (no TMA loads of the A operand)
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
-  bool cluster2 = false; // FDSR_CLUSTER=1: 2-CTA clusters with multicast weight stages (measured twice: no gain)
-  cudaGraphExec_t graph = nullptr;
-  struct {
-    int B = 0, H = 0, W = 0;
-    const void* noise = nullptr;
-    void* trace = nullptr;
-  } gkey;
+  bool pair = true;      // FDSR_PAIR=0: never launch CTA pairs (cta_group::2); every layer runs the single-CTA kernel
+  // Captured sampling loops, keyed on what the captured launches depend on: the shape and whether noise is injected /
+  // a trace is written.  Seed, image offset and the noise / trace POINTERS are read from device memory (SampleArgs),
+  // so a fresh noise tensor, a new seed or a ragged last batch followed by a full one never forces a re-capture.
+  struct GraphEntry {
+    int B, H, W;
+    bool noise, trace;
+    cudaGraphExec_t exec;
+    uint64_t used;
+    int64_t launches;   // kernels per replay
+  };
+  std::vector<GraphEntry> graphs;   // small LRU (kMaxGraphs)
+  uint64_t graph_clock = 0;
+  int64_t graph_captures = 0;
+  uint64_t image0 = 0;              // fdsr_set_image_offset
+  size_t ws_cap = 0;                // allocated bytes of d_ws (grow-only: cached graphs hold pointers into it)
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   int64_t launches = 0;
   double flops_per_px = 0.0;  // conv FLOPs per full-resolution output pixel per image
 };
@@ -501,6 +517,63 @@ int build_plan(fdsr_ctx* c) {
   return FDSR_OK;
 }
 
+const std::vector<float>* find_w(fdsr_ctx* c, const std::string& name);
+
+// Exact element counts of every tensor the plan reads, before anything indexes into them: the C ABI is a public
+// boundary that does not go through torch's strict shape check, and a state_dict of a different inner_channel /
+// channel_mults must be refused by name, not read out of bounds (model/model.py:159-160 raises in the same situation).
+int validate_weights(fdsr_ctx* c) {
+  auto need = [&](const std::string& name, size_t numel, const char* what) -> int {
+    const auto* w = find_w(c, name);
+    if (!w) return fail(c, FDSR_E_NOTFOUND, "state_dict is missing %s", name.c_str());
+    if (w->size() != numel)
+      return fail(c, FDSR_E_INVALID, "%s: %s has %zu elements, the configured network needs %zu", what, name.c_str(),
+                  w->size(), numel);
+    return FDSR_OK;
+  };
+  const size_t inner = size_t(c->cfg.inner_channel);
+  int rc;
+  // conv weights: rows x (sum of the source channels this weight tensor spans) x k x k
+  std::map<std::string, size_t> cin_of, rows_of, kk_of;
+  for (const HConv& k : c->convs)
+    for (const HChunk& ch : k.chunks) {
+      if (ch.wname == "@identity") continue;
+      size_t& ci = cin_of[ch.wname];
+      ci = std::max(ci, size_t(ch.wc0 + ch.creal));
+      rows_of[ch.wname] = size_t(k.w_rows ? k.w_rows : k.cout);
+      kk_of[ch.wname] = size_t(ch.kk);
+    }
+  for (const auto& it : cin_of)
+    if ((rc = need(it.first, rows_of[it.first] * it.second * kk_of[it.first] * kk_of[it.first], "conv weight"))) return rc;
+  for (const HConv& k : c->convs) {
+    for (const std::string& bn : k.bias_names)
+      if ((rc = need(bn, size_t(k.cout), "conv bias"))) return rc;
+    if (k.gn_C) {
+      if ((rc = need(k.gn_name + ".weight", size_t(k.gn_C), "GroupNorm weight"))) return rc;
+      if ((rc = need(k.gn_name + ".bias", size_t(k.gn_C), "GroupNorm bias"))) return rc;
+    }
+    if (!k.film_name.empty()) {  // FeatureWiseAffine / ResnetBlock.mlp: Linear(inner -> cout)
+      if ((rc = need(k.film_name + ".weight", size_t(k.cout) * inner, "FiLM weight"))) return rc;
+      if ((rc = need(k.film_name + ".bias", size_t(k.cout), "FiLM bias"))) return rc;
+    }
+  }
+  // noise_level_mlp / time_mlp: Linear(inner -> 4 inner), Swish, Linear(4 inner -> inner)
+  const std::string mlp = c->cfg.model == FDSR_MODEL_SR3 ? "denoise_fn.time_mlp" : "denoise_fn.noise_level_mlp";
+  if ((rc = need(mlp + ".1.weight", 4 * inner * inner, "embedding MLP"))) return rc;
+  if ((rc = need(mlp + ".1.bias", 4 * inner, "embedding MLP"))) return rc;
+  if ((rc = need(mlp + ".3.weight", 4 * inner * inner, "embedding MLP"))) return rc;
+  if ((rc = need(mlp + ".3.bias", inner, "embedding MLP"))) return rc;
+  for (const HAttn& a : c->attns) {
+    if (a.kind != 0) continue;  // CLAM: Conv2d(C, C/16, 1), Conv2d(C/16, C, 1); SLAM: Conv2d(2, 1, 7) — all bias-free
+    const std::string q = "denoise_fn." + a.name;
+    const size_t C = size_t(a.C), R = C / 16;
+    if ((rc = need(q + ".ca.fc1.weight", R * C, "CLAM fc1"))) return rc;
+    if ((rc = need(q + ".ca.fc2.weight", C * R, "CLAM fc2"))) return rc;
+    if ((rc = need(q + ".sa.conv1.weight", 98, "SLAM conv"))) return rc;
+  }
+  return FDSR_OK;
+}
+
 const std::vector<float>* find_w(fdsr_ctx* c, const std::string& name) {
   if (name == "@identity") {  // 256 x 256 identity (1x1 "weights" of an identity-residual K chunk)
     static const std::vector<float> eye = [] {
@@ -520,14 +593,32 @@ template <>
 __half to_t<__half>(float f) { return __float2half_rn(f); }
 template <>
 __nv_bfloat16 to_t<__nv_bfloat16>(float f) { return __float2bfloat16_rn(f); }
+// weight of a chunk whose A operand is a GroupNorm output: always fp16 (GnOperand, conv_kernel.cuh); raw chunks: T
+template <typename T>
+T to_w(float f, bool gn_chunk) {
+  if (!gn_chunk) return to_t<T>(f);
+  const __half h = __float2half_rn(f);
+  T r;
+  static_assert(sizeof(T) == sizeof(__half), "16-bit storage");
+  memcpy(&r, &h, sizeof r);
+  return r;
+}
 
 template <typename T>
 int pack_weights(fdsr_ctx* c) {
   // blob layout per (chunk, tap): [channel group][n][8 channels] of T  (K-major, no swizzle)
+  // Pair-capable layers are packed twice: the full-width layout (single-CTA launches, split-N halves) and, at w_off2,
+  // two half-width copies of the same layout — columns [0, N/2) then [N/2, N) — for CTA-pair launches.
   size_t total = 0;
   for (HConv& k : c->convs) {
     k.w_off = total;
-    for (const HChunk& ch : k.chunks) total += size_t(k.phases) * ch.taps.size() * size_t(k.ncg) * k.N * 16;
+    k.w_bytes = 0;
+    for (const HChunk& ch : k.chunks) k.w_bytes += size_t(k.phases) * ch.taps.size() * size_t(k.ncg) * k.N * 16;
+    total += k.w_bytes;
+  }
+  for (HConv& k : c->convs) {
+    k.w_off2 = total;
+    if (k.pair_ok()) total += k.w_bytes;
   }
   std::vector<T> host(total / sizeof(T), to_t<T>(0.f));
   for (HConv& k : c->convs) {
@@ -555,14 +646,25 @@ int pack_weights(fdsr_ctx* c) {
                   for (int dx = 0; dx < 3; ++dx)
                     if (((py + dy + 1) >> 1) - py == tp.ky && ((px + dx + 1) >> 1) - px == tp.kx)
                       acc += (*w)[wbase + dy * 3 + dx];
-                blob[(size_t(cg) * k.N + n) * 8 + j] = to_t<T>(acc);
+                blob[(size_t(cg) * k.N + n) * 8 + j] = to_w<T>(acc, ch.gn != 0);
                 continue;
               }
               const size_t wi = wbase + (is1x1 ? 0 : tp.ky) * kk + (is1x1 ? 0 : tp.kx);
-              blob[(size_t(cg) * k.N + n) * 8 + j] = to_t<T>((*w)[wi]);
+              blob[(size_t(cg) * k.N + n) * 8 + j] = to_w<T>((*w)[wi], ch.gn != 0);
             }
         off += size_t(k.ncg) * k.N * 16;
       }
+    }
+    if (k.pair_ok()) {  // half-width copies: element (blob, cg, n, j) -> half n / (N/2), same blob, (cg, n % (N/2), j)
+      const size_t blob_e = size_t(k.ncg) * k.N * 8, nblobs = k.w_bytes / (blob_e * sizeof(T));
+      const int nh = k.N / 2;
+      const T* src = host.data() + k.w_off / sizeof(T);
+      T* dst = host.data() + k.w_off2 / sizeof(T);
+      for (size_t bi = 0; bi < nblobs; ++bi)
+        for (int cg = 0; cg < k.ncg; ++cg)
+          for (int n = 0; n < k.N; ++n)
+            memcpy(dst + size_t(n / nh) * (nblobs * blob_e / 2) + bi * (blob_e / 2) + (size_t(cg) * nh + n % nh) * 8,
+                   src + bi * blob_e + (size_t(cg) * k.N + n) * 8, 8 * sizeof(T));
     }
   }
   if (c->d_weights) cudaFree(c->d_weights);
@@ -733,6 +835,7 @@ int build_bias_tables(fdsr_ctx* c) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t kOffFlags = 64;  // status word inside the fixed first 256 bytes of the workspace (after SampleArgs)
 
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -958,7 +1061,7 @@ int upload_layers(fdsr_ctx* c) {
     // Split-N: a low-resolution layer with fewer 256-pixel tiles than half the SMs is computed as two
     // 128-column halves by twice as many CTAs.  Only 256 -> 2 x 128: both widths use the same
     // per-tile statistics path, so results stay bitwise independent of the batch size.
-    l.nsplit = (c->split_n && k.out_mode == kOutAct && k.N == 256 && !c->cluster2 &&
+    l.nsplit = (c->split_n && k.out_mode == kOutAct && k.N == 256 &&
                 (2 * l.ntiles <= c->num_sms || c->split_all)) ? 2 : 1;
     l.n_full = k.N;
     l.N = k.N / l.nsplit;
@@ -1037,13 +1140,19 @@ int upload_layers(fdsr_ctx* c) {
     } else {
       l.out = c->d_ws + c->off_eps;
     }
-    l.weights = c->d_weights + k.w_off;
+    // CTA pairs (cta_group::2): TMA-fed layers whose tile rows have an even number of tiles (a pair = two x-neighbours);
+    // the choice depends on the layer and the image shape only, never on B, so results do not depend on the batch size
+    l.pair = (c->pair && k.pair_ok() && l.a_tma && l.nsplit == 1 && l.tiles_x % 2 == 0) ? 1 : 0;
+    l.weights = c->d_weights + (l.pair ? k.w_off2 : k.w_off);
+    l.w_half = int32_t(k.w_bytes / 2);
     {
       const int tpi = l.tiles_x * l.tiles_y;
-      // running TMEM statistics exist for N = 64 only; the group size must not depend on B
-      l.group = (l.N == 64 && tpi % 2 == 0) ? 2 : 1;
+      // running TMEM statistics exist for N = 64 only; the group size must not depend on B.  A CTA's consecutive tiles
+      // are t, t+1 (single) or t, t+2 (pair): both of a group must belong to one image
+      l.group = (l.N == 64 && tpi % (l.pair ? 4 : 2) == 0) ? 2 : 1;
     }
     l.prof = c->d_prof;
+    l.flags = reinterpret_cast<unsigned int*>(c->d_ws + kOffFlags);
     {
       const char* e = getenv("FDSR_DBG_SKIP");
       l.dbg = e ? atoi(e) : 0;
@@ -1059,11 +1168,19 @@ int upload_layers(fdsr_ctx* c) {
 
 template <int N, typename T>
 cudaError_t set_conv_attr() {
-  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        ConvCfg<N>::kSmemBytes);
-  if (e == cudaSuccess && Cvt<T>::kFmt == 0)
-    e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, Cvt<T>::kFmt == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ConvCfg<N>::kSmemBytes);
+  if constexpr (N >= 64) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ConvCfg<N>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ConvCfg<N>::kSmemBytes);
+  }
   return e;
 }
 template <typename T>
@@ -1080,12 +1197,11 @@ int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st);
 
 template <int N, typename T>
 int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
-  const int ngroups = ntiles / c->h_layers[li].group;
+  const bool pair = c->h_layers[li].pair != 0;
+  const int cs = pair ? 2 : 1;  // CTA pairs are clusters of two; the unit of work is then a pair of tiles
+  const int ngroups = ntiles / cs / c->h_layers[li].group;
   const int nsplit = c->h_layers[li].nsplit;
-  // clusters of 2 CTAs share (multicast) the weight stages; needs an even number of groups
-  const int cs = (c->cluster2 && ngroups % 2 == 0 && ngroups >= 2) ? 2 : 1;
-  int grid = ngroups < c->num_sms ? ngroups : c->num_sms;
-  grid -= grid % cs;
+  int grid = (ngroups < c->num_sms / cs ? ngroups : c->num_sms / cs) * cs;
   if (nsplit > 1) {  // nsplit CTAs per tile group; persistent over the groups when there are more than fit one wave
     grid = ngroups * nsplit;
     if (grid > c->num_sms) grid = c->num_sms - c->num_sms % nsplit;
@@ -1104,10 +1220,20 @@ int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = c->pdl ? 2 : 1;
-  if (Cvt<T>::kFmt == 0 && !c->precise)
-    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, Cvt<T>::kFmt == 0>, c->h_layers[li], t));
+  const bool fast = !c->precise;
+  if constexpr (N >= 64) {
+    if (pair) {
+      if (fast) CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, true, true>, c->h_layers[li], t));
+      else CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false, true>, c->h_layers[li], t));
+      CUDA_TRY(c, cudaGetLastError());
+      ++c->launches;
+      return FDSR_OK;
+    }
+  }
+  if (fast)
+    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, true, false>, c->h_layers[li], t));
   else
-    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false>, c->h_layers[li], t));
+    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false, false>, c->h_layers[li], t));
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
   return FDSR_OK;
@@ -1229,18 +1355,24 @@ int check_ready(fdsr_ctx* c) {
   return FDSR_OK;
 }
 
+// x_{t-1} from (x_t, eps): `images` blocks of numel_img floats.  z: explicit tensor, or (args) block z_block of the
+// injected noise / the generator's stream t
 int posterior_launch(fdsr_ctx* c, const float* x, const float* eps, const float* z, int t, float* out,
-                     int64_t numel, const uint64_t* seed, cudaStream_t st) {
-  if (numel % 4) return fail(c, FDSR_E_INVALID, "numel must be a multiple of 4");
-  const int64_t n4 = numel / 4;
-  posterior_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(x, eps, z, out, n4, c->post[t], seed, uint32_t(t));
+                     int64_t numel_img, int images, const SampleArgs* args, int64_t z_block, cudaStream_t st) {
+  if (numel_img % 4 || numel_img / 4 > 0x7fffffffLL || images < 1 || images > 65535)
+    return fail(c, FDSR_E_INVALID, "posterior: per-image element count must be a multiple of 4 (< 2^33), 1..65535 images");
+  const uint32_t n4 = uint32_t(numel_img / 4);
+  posterior_kernel<<<dim3((n4 + 255) / 256, images), 256, 0, st>>>(x, eps, z, out, n4, c->post[t], args, z_block,
+                                                                    uint32_t(t), t > 0 ? 1 : 0);
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
   return FDSR_OK;
 }
 
-int sample_enqueue(fdsr_ctx* c, const float* noise, float* trace, cudaStream_t st) {
-  const uint64_t* seed = reinterpret_cast<const uint64_t*>(c->d_ws + c->off_seed);
+// The T-step loop on the context's buffers.  Everything that differs between two calls of the same shape (seed,
+// image offset, noise / trace pointers) is read from the SampleArgs slot in device memory.
+int sample_enqueue(fdsr_ctx* c, bool has_noise, bool has_trace, cudaStream_t st) {
+  const SampleArgs* args = reinterpret_cast<const SampleArgs*>(c->d_ws + c->off_seed);
   const int T = c->T, B = c->B;
   const int64_t per = int64_t(3) * c->H * c->W, numel = per * B;
   float* x = reinterpret_cast<float*>(c->d_ws + c->off_x);
@@ -1249,54 +1381,35 @@ int sample_enqueue(fdsr_ctx* c, const float* noise, float* trace, cudaStream_t s
   float* sr = reinterpret_cast<float*>(c->d_ws + c->off_sr);
   const int nfr = fdsr_trace_frames(c);
   const unsigned gb = unsigned((numel + 255) / 256);
-  if (noise) {
-    CUDA_TRY(c, cudaMemcpyAsync(x, noise, numel * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    noise_fill_kernel<<<unsigned((numel / 4 + 255) / 256), 256, 0, st>>>(x, numel / 4, seed, uint32_t(T));
-    ++c->launches;
-  }
+  const uint32_t n4 = uint32_t(per / 4);
+  noise_init_kernel<<<dim3((n4 + 255) / 256, B), 256, 0, st>>>(x, n4, args, uint32_t(T));
+  ++c->launches;
   // FastDiffSR predicts the residual: frames and result go through res2img (diffusion.py:213-216, 275-281).
   // The SR3 baseline predicts the image: frames are the raw x, the first frame is the conditioning image itself
   // (ddpm_modules/diffusion.py:218-227).
-  const bool sr3 = c->cfg.model == FDSR_MODEL_SR3;
-  auto copy_frame = [&](const float* src, float* dst, size_t dst_stride) {  // B images of `per` floats
-    return cudaMemcpy2DAsync(dst, dst_stride * 4, src, size_t(per) * 4, size_t(per) * 4, size_t(B),
-                             cudaMemcpyDeviceToDevice, st);
-  };
+  const int sr3 = c->cfg.model == FDSR_MODEL_SR3 ? 1 : 0;
   int frame = 0;
-  if (trace) {
-    if (sr3) {
-      CUDA_TRY(c, copy_frame(cond, trace, size_t(per) * nfr));
-    } else {
-      res2img_kernel<<<gb, 256, 0, st>>>(cond, cond, trace, per, per * nfr, B);
-      ++c->launches;
-    }
+  if (has_trace) {
+    res2img_kernel<<<gb, 256, 0, st>>>(cond, cond, nullptr, per, per * nfr, B, args, 0, sr3);
+    ++c->launches;
     frame = 1;
   }
   const int inter = 1 | (T / 10);
   for (int k = 0, t = T - 1; t >= 0; --t, ++k) {
     int rc = unet_dispatch(c, t, st);
     if (rc) return rc;
-    const float* z = (noise && t > 0) ? noise + int64_t(k + 1) * numel : nullptr;
-    rc = posterior_launch(c, x, eps, z, t, x, numel, (!noise && t > 0) ? seed : nullptr, st);
+    rc = posterior_launch(c, x, eps, nullptr, t, x, per, B, args, k + 1, st);
     if (rc) return rc;
-    if (trace && t % inter == 0) {
-      if (sr3) {
-        CUDA_TRY(c, copy_frame(x, trace + per * frame, size_t(per) * nfr));
-      } else {
-        res2img_kernel<<<gb, 256, 0, st>>>(x, cond, trace + per * frame, per, per * nfr, B);
-        ++c->launches;
-      }
+    if (has_trace && t % inter == 0) {
+      res2img_kernel<<<gb, 256, 0, st>>>(x, cond, nullptr, per, per * nfr, B, args, per * frame, sr3);
+      ++c->launches;
       ++frame;
     }
   }
-  if (sr3) {
-    CUDA_TRY(c, cudaMemcpyAsync(sr, x, size_t(numel) * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    res2img_kernel<<<gb, 256, 0, st>>>(x, cond, sr, per, per, B);
-    ++c->launches;
-  }
+  res2img_kernel<<<gb, 256, 0, st>>>(x, cond, sr, per, per, B, args, 0, sr3);
+  ++c->launches;
   CUDA_TRY(c, cudaGetLastError());
+  (void)has_noise;
   return FDSR_OK;
 }
 
@@ -1381,8 +1494,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->precise = e && e[0] == '1';
     const char* e2 = getenv("FDSR_TMA_STORE");
     c->tma_store = !(e2 && e2[0] == '0');
-    const char* e3 = getenv("FDSR_CLUSTER");
-    c->cluster2 = e3 && e3[0] == '1';
+    const char* e3 = getenv("FDSR_PAIR");
+    c->pair = !(e3 && e3[0] == '0');
     const char* e4 = getenv("FDSR_SPLIT_N");
     c->split_n = !(e4 && e4[0] == '0');
     const char* e5 = getenv("FDSR_PDL");
@@ -1425,7 +1538,7 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
 
 int fdsr_destroy(fdsr_ctx* c) {
   if (!c) return FDSR_OK;
-  if (c->graph) cudaGraphExecDestroy(c->graph);
+  c->drop_graphs();
   cudaFree(c->d_weights);
   cudaFree(c->d_weights32);
   cudaFree(c->d_params);
@@ -1449,26 +1562,24 @@ int fdsr_load_weights(fdsr_ctx* c, const char* const* names, const float* const*
                       int32_t n) {
   if (!c || !names || !ptrs || !numels) return fail(c, FDSR_E_INVALID, "null argument");
   c->host_w.clear();
-  for (int i = 0; i < n; ++i) c->host_w[names[i]] = std::vector<float>(ptrs[i], ptrs[i] + numels[i]);
-  // shape checks against the plan
-  for (const HConv& k : c->convs)
-    for (const HChunk& ch : k.chunks) {
-      const auto* w = find_w(c, ch.wname);
-      if (!w) return fail(c, FDSR_E_NOTFOUND, "state_dict is missing %s", ch.wname.c_str());
-      if (w->size() % (size_t(k.w_rows ? k.w_rows : k.cout) * ch.kk * ch.kk) != 0)
-        return fail(c, FDSR_E_INVALID, "unexpected size for %s", ch.wname.c_str());
-    }
-  int rc = c->cfg.dtype == FDSR_DTYPE_FP32 ? pack_weights_f32(c)
-           : c->cfg.dtype == FDSR_DTYPE_BF16 ? pack_weights<__nv_bfloat16>(c) : pack_weights<__half>(c);
+  for (int i = 0; i < n; ++i) {
+    if (!names[i] || !ptrs[i] || numels[i] < 0) return fail(c, FDSR_E_INVALID, "null / negative entry %d", i);
+    c->host_w[names[i]] = std::vector<float>(ptrs[i], ptrs[i] + numels[i]);
+  }
+  int rc = validate_weights(c);
+  if (rc) {
+    c->host_w.clear();
+    c->weights_loaded = false;
+    return rc;
+  }
+  rc = c->cfg.dtype == FDSR_DTYPE_FP32 ? pack_weights_f32(c)
+       : c->cfg.dtype == FDSR_DTYPE_BF16 ? pack_weights<__nv_bfloat16>(c) : pack_weights<__half>(c);
   if (rc) return rc;
   rc = upload_params(c);
   if (rc) return rc;
   c->weights_loaded = true;
   c->layers_dirty = true;
-  if (c->graph) {
-    cudaGraphExecDestroy(c->graph);
-    c->graph = nullptr;
-  }
+  c->drop_graphs();
   if (c->T) return build_bias_tables(c);
   return FDSR_OK;
 }
@@ -1517,10 +1628,7 @@ int fdsr_set_schedule(fdsr_ctx* c, const double* betas, int32_t T) {
   c->post.resize(T);
   for (int i = 0; i < T; ++i)
     c->post[i] = PostCoef{float(s_r[i]), float(s_rm1[i]), float(c1[i]), float(c2[i]), expf(0.5f * float(plv[i]))};
-  if (c->graph) {
-    cudaGraphExecDestroy(c->graph);
-    c->graph = nullptr;
-  }
+  c->drop_graphs();
   return build_bias_tables(c);
 }
 
@@ -1539,7 +1647,8 @@ int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
   if (B < 1 || H < down || W < down || H % down || W % down)
     return fail(c, FDSR_E_INVALID, "B>=1 and H, W multiples of %d required (got %dx%dx%d)", down, B, H, W);
   if (c->B == B && c->H == H && c->W == W && c->d_ws) return FDSR_OK;
-  size_t off = 0;
+  // per-call sampler arguments and the overflow flag sit at the start so that they never move
+  size_t off = 256;
   for (HTensor& t : c->tensors) {
     t.off = off;
     off = align_up(off + size_t(B) * (H >> t.level) * (W >> t.level) * t.C * c->esize(), 256);
@@ -1576,22 +1685,25 @@ int fdsr_reserve(fdsr_ctx* c, int32_t B, int32_t H, int32_t W) {
   off += img;
   c->off_sr = off;
   off += img;
-  c->off_seed = off;
-  off += 256;
+  c->off_seed = 0;
   c->off_gntab = off;
   off += c->cfg.dtype == FDSR_DTYPE_FP32 ? size_t(B) * kMaxGnC * 8 : 0;
-  if (c->d_ws) cudaFree(c->d_ws);
-  c->d_ws = nullptr;
-  CUDA_TRY(c, cudaMalloc(&c->d_ws, off));
+  // grow-only: the captured graphs of other shapes hold pointers into the workspace and stay valid as long as it is
+  // not reallocated (alternating shapes / a ragged last batch re-use their graphs)
+  if (off > c->ws_cap) {
+    c->drop_graphs();
+    if (c->d_ws) cudaFree(c->d_ws);
+    c->d_ws = nullptr;
+    c->ws_cap = 0;
+    CUDA_TRY(c, cudaMalloc(&c->d_ws, off));
+    CUDA_TRY(c, cudaMemset(c->d_ws, 0, 256));
+    c->ws_cap = off;
+  }
   c->ws_bytes = off;
   c->B = B;
   c->H = H;
   c->W = W;
   c->layers_dirty = true;
-  if (c->graph) {
-    cudaGraphExecDestroy(c->graph);
-    c->graph = nullptr;
-  }
   return FDSR_OK;
 }
 
@@ -1620,7 +1732,12 @@ int fdsr_posterior_step(fdsr_ctx* c, const float* xt, const float* eps, const fl
   if (!c || !xt || !eps || !out) return fail(c, FDSR_E_INVALID, "null argument");
   if (c->T == 0) return fail(c, FDSR_E_STATE, "fdsr_set_schedule has not been called");
   if (t < 0 || t >= c->T) return fail(c, FDSR_E_INVALID, "t out of range");
-  return posterior_launch(c, xt, eps, t > 0 ? z : nullptr, t, out, numel, nullptr, static_cast<cudaStream_t>(stream));
+  if (t > 0 && !z) return fail(c, FDSR_E_INVALID, "z is required for t > 0");
+  if (numel < 4 || numel % 4) return fail(c, FDSR_E_INVALID, "numel must be a positive multiple of 4");
+  // one "image" of numel floats when it fits the per-image limit, else split into equal blocks
+  int64_t blocks = 1;
+  while (numel % blocks != 0 || (numel / blocks) / 4 > 0x7fffffffLL) ++blocks;
+  return posterior_launch(c, xt, eps, z, t, out, numel / blocks, int(blocks), nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 int32_t fdsr_trace_frames(const fdsr_ctx* c) {
@@ -1642,8 +1759,9 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t bytes = size_t(B) * 3 * H * W * 4;
   CUDA_TRY(c, cudaMemcpyAsync(c->d_ws + c->off_cond, cond, bytes, cudaMemcpyDeviceToDevice, st));
-  // the Philox seed is read from device memory, so one captured graph serves every seed
-  set_seed_kernel<<<1, 1, 0, st>>>(reinterpret_cast<uint64_t*>(c->d_ws + c->off_seed), seed);
+  // seed, image offset and the noise / trace pointers are read from device memory: one captured graph per shape
+  SampleArgs a{seed, c->image0, noise, trace};
+  set_args_kernel<<<1, 1, 0, st>>>(reinterpret_cast<SampleArgs*>(c->d_ws + c->off_seed), a);
   ++c->launches;
   // a T = 1000 schedule would be a graph of ~10^5 nodes: long schedules are enqueued directly (the host runs
   // far ahead of the device: ~0.3 ms of launch calls per ~5 ms UNet step)
@@ -1653,48 +1771,46 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
       rc = upload_layers(c);
       if (rc) return rc;
     }
-    const bool hit = c->graph && c->gkey.B == B && c->gkey.H == H && c->gkey.W == W && c->gkey.noise == noise &&
-                     c->gkey.trace == trace;
+    fdsr_ctx::GraphEntry* hit = nullptr;
+    for (auto& g : c->graphs)
+      if (g.B == B && g.H == H && g.W == W && g.noise == (noise != nullptr) && g.trace == (trace != nullptr)) hit = &g;
     if (!hit) {
-      if (c->graph) {
-        cudaGraphExecDestroy(c->graph);
-        c->graph = nullptr;
+      constexpr size_t kMaxGraphs = 8;
+      if (c->graphs.size() >= kMaxGraphs) {  // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < c->graphs.size(); ++i)
+          if (c->graphs[i].used < c->graphs[lru].used) lru = i;
+        cudaGraphExecDestroy(c->graphs[lru].exec);
+        c->graphs.erase(c->graphs.begin() + lru);
       }
       cudaStream_t cs;
       CUDA_TRY(c, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      // make sure every kernel attribute is set before capture (cudaFuncSetAttribute is not capturable)
       const int64_t l0 = c->launches;
       CUDA_TRY(c, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      rc = sample_enqueue(c, noise, trace, cs);
+      rc = sample_enqueue(c, noise != nullptr, trace != nullptr, cs);
       cudaGraph_t g = nullptr;
       cudaError_t e = cudaStreamEndCapture(cs, &g);
       cudaStreamDestroy(cs);
+      const int64_t per_replay = c->launches - l0;
+      c->launches = l0;  // captured, not yet launched
       if (rc) {
         if (g) cudaGraphDestroy(g);
         return rc;
       }
       if (e != cudaSuccess) return fail(c, FDSR_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-      e = cudaGraphInstantiate(&c->graph, g, 0);
+      cudaGraphExec_t exec = nullptr;
+      e = cudaGraphInstantiate(&exec, g, 0);
       cudaGraphDestroy(g);
       if (e != cudaSuccess) return fail(c, FDSR_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-      c->gkey.B = B;
-      c->gkey.H = H;
-      c->gkey.W = W;
-      c->gkey.noise = noise;
-      c->gkey.trace = trace;
-      c->launches = l0;  // captured, not yet launched
+      c->graphs.push_back({B, H, W, noise != nullptr, trace != nullptr, exec, 0, per_replay});
+      hit = &c->graphs.back();
+      ++c->graph_captures;
     }
-    CUDA_TRY(c, cudaGraphLaunch(c->graph, st));
-    // launches per replay: recompute deterministically
-    int per_unet = 1;
-    for (const HOp& op : c->ops)
-      per_unet += op.kind != 0 ? (c->attns[op.idx].kind == 0 ? 4 : 1)
-                               : ((c->cfg.dtype == FDSR_DTYPE_FP32 && c->convs[op.idx].gn_C) ? 2 : 1);
-    const bool sr3 = c->cfg.model == FDSR_MODEL_SR3;  // (its frames and result are copies, not kernels)
-    c->launches += int64_t(c->T) * (per_unet + 1) + (sr3 ? 0 : 1) + (noise ? 0 : 1) +
-                   ((trace && !sr3) ? fdsr_trace_frames(c) : 0);
+    hit->used = ++c->graph_clock;
+    CUDA_TRY(c, cudaGraphLaunch(hit->exec, st));
+    c->launches += hit->launches;
   } else {
-    rc = sample_enqueue(c, noise, trace, st);
+    rc = sample_enqueue(c, noise != nullptr, trace != nullptr, st);
     if (rc) return rc;
   }
   CUDA_TRY(c, cudaMemcpyAsync(sr_out, c->d_ws + c->off_sr, bytes, cudaMemcpyDeviceToDevice, st));
@@ -1759,7 +1875,8 @@ int fdsr_super_resolve_u8(fdsr_ctx* c, const uint8_t* lr_host, int32_t B, int32_
   rc = fdsr_sample(c, d_cond, noise_dev, seed, d_sr, nullptr, B, H, W, stream);
   if (rc) return rc;
   CUDA_TRY(c, cudaMemcpyAsync(h_sr, d_sr, out_b, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(c, cudaStreamSynchronize(st));
+  rc = fdsr_check_overflow(c, stream);  // (synchronises the stream)
+  if (rc) return rc;
   memcpy(sr_out_host, h_sr, out_b);
   return FDSR_OK;
 }
@@ -1913,6 +2030,48 @@ int fdsr_debug_role_cycles(fdsr_ctx* c, int32_t op, int32_t t, int64_t* out_host
   CUDA_TRY(c, cudaStreamSynchronize(st));
   return n;
 }
+
+int fdsr_check_overflow(fdsr_ctx* c, void* stream) {
+  if (!c) return FDSR_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!c->d_ws) {
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return FDSR_OK;
+  }
+  unsigned int flags = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&flags, c->d_ws + kOffFlags, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (flags & 1u) {
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ws + kOffFlags, 0, 4, st));
+    return fail(c, FDSR_E_OVERFLOW, "fp16 overflow: an activation exceeded +-65504 and was stored saturated; the result is "
+                                    "not trustworthy -- create the context with FDSR_DTYPE_BF16 for this network");
+  }
+  return FDSR_OK;
+}
+
+int fdsr_set_image_offset(fdsr_ctx* c, uint64_t first_image) {
+  if (!c) return FDSR_E_INVALID;
+  c->image0 = first_image;
+  return FDSR_OK;
+}
+
+int fdsr_debug_noise(fdsr_ctx* c, float* out, int32_t B, int32_t H, int32_t W, uint64_t seed, uint64_t first_image,
+                     int32_t stream_id, void* stream) {
+  if (!c || !out || B < 1 || B > 65535 || H < 1 || W < 1 || (int64_t(3) * H * W) % 4)
+    return fail(c, FDSR_E_INVALID, "bad argument (3*H*W must be a multiple of 4)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SampleArgs* slot = nullptr;  // a private argument slot: the workspace may not exist yet
+  CUDA_TRY(c, cudaMallocAsync(reinterpret_cast<void**>(&slot), sizeof(SampleArgs), st));
+  set_args_kernel<<<1, 1, 0, st>>>(slot, SampleArgs{seed, first_image, nullptr, nullptr});
+  const uint32_t n4 = uint32_t(int64_t(3) * H * W / 4);
+  noise_init_kernel<<<dim3((n4 + 255) / 256, B), 256, 0, st>>>(out, n4, slot, uint32_t(stream_id));
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaFreeAsync(slot, st));
+  c->launches += 2;
+  return FDSR_OK;
+}
+
+int64_t fdsr_graph_captures(const fdsr_ctx* c) { return c ? c->graph_captures : 0; }
 
 int64_t fdsr_launch_count(const fdsr_ctx* c) { return c ? c->launches : 0; }
 double fdsr_unet_flops(const fdsr_ctx* c) { return c ? c->flops_per_px * double(c->B) * c->H * c->W : 0.0; }

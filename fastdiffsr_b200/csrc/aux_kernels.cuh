@@ -10,7 +10,10 @@
 namespace fdsr {
 
 // ------------------------------------------------------------------------------------------
-// Counter-based Gaussian noise: Philox4x32-10 keyed by the seed, counter = (element/4, stream).
+// Counter-based Gaussian noise: Philox4x32-10 keyed by the seed.  The counter is (position inside the image / 4,
+// GLOBAL image index, stream): the noise of an image depends on the seed, the image's index in the whole job and
+// the step only — not on the batch it happens to be sampled in, nor on which rank samples it — so a batch sharded
+// over N ranks reproduces the single-rank result bit for bit.  Streams: T for x_T, t for the z of step t.
 // Used when the caller does not inject noise (the reference draws torch.randn on the device,
 // diffusion.py:189,207; any N(0,1) stream is an equally valid sample of the same sampler).
 // ------------------------------------------------------------------------------------------
@@ -25,8 +28,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream, uint64_t idx4) {
-  const uint4 r = philox4x32_10(make_uint4(uint32_t(idx4), uint32_t(idx4 >> 32), stream, 0x5eedu),
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream, uint64_t image, uint32_t idx4) {
+  const uint4 r = philox4x32_10(make_uint4(idx4, uint32_t(image), stream, 0x5eedu + uint32_t(image >> 32)),
                                 make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
   const float k = 2.3283064365386963e-10f;  // 2^-32
   const float u0 = (float(r.x) + 0.5f) * k, u1 = (float(r.y) + 0.5f) * k;
@@ -38,13 +41,25 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream,
   return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
 }
 
-// The seed lives in device memory so that a captured CUDA graph can be replayed with a new seed.
-__global__ void set_seed_kernel(uint64_t* slot, uint64_t seed) { *slot = seed; }
+// Per-call arguments of the sampler that live in DEVICE memory, so that one captured CUDA graph per
+// (B, H, W, injected-noise?, trace?) serves every seed, image offset, noise tensor and trace tensor.
+struct SampleArgs {
+  uint64_t seed;         // Philox key
+  uint64_t image0;       // global index of the first image of this batch
+  const float* noise;    // (T,B,3,H,W) injected noise, or null: built-in generator
+  float* trace;          // (B, frames, 3, H, W), or null
+};
+__global__ void set_args_kernel(SampleArgs* slot, SampleArgs a) { *slot = a; }
 
-__global__ void noise_fill_kernel(float* __restrict__ out, int64_t n4, const uint64_t* __restrict__ seed,
+// x_T: the first (B,3,H,W) block of the injected noise, or stream T of the generator.  grid (n4_img / 256, B)
+__global__ void noise_init_kernel(float* __restrict__ out, uint32_t n4_img, const SampleArgs* __restrict__ args,
                                   uint32_t stream) {
-  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i < n4) reinterpret_cast<float4*>(out)[i] = philox_normal4(*seed, stream, i);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4_img) return;
+  const size_t o = size_t(blockIdx.y) * n4_img + i;
+  const float* nz = args->noise;
+  reinterpret_cast<float4*>(out)[o] = nz != nullptr ? reinterpret_cast<const float4*>(nz)[o]
+                                                    : philox_normal4(args->seed, stream, args->image0 + blockIdx.y, i);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -105,34 +120,46 @@ __device__ __forceinline__ float post1(float x, float e, float z, const PostCoef
   const float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, x));
   return __fadd_rn(mean, __fmul_rn(z, k.sigma));
 }
+// grid (n4_img / 256, B).  z: explicit tensor (fdsr_posterior_step), else block `z_block` of args->noise, else the
+// generator's stream `stream`; add_noise = 0 (t == 0): z = 0.
 __global__ void posterior_kernel(const float* __restrict__ x, const float* __restrict__ eps,
-                                 const float* __restrict__ z, float* __restrict__ out, int64_t n4,
-                                 PostCoef k, const uint64_t* __restrict__ seed, uint32_t stream) {
-  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i >= n4) return;
-  const float4 xv = reinterpret_cast<const float4*>(x)[i];
-  const float4 ev = reinterpret_cast<const float4*>(eps)[i];
+                                 const float* __restrict__ z, float* __restrict__ out, uint32_t n4_img,
+                                 PostCoef k, const SampleArgs* __restrict__ args, int64_t z_block, uint32_t stream,
+                                 int add_noise) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4_img) return;
+  const size_t o = size_t(blockIdx.y) * n4_img + i;
+  const float4 xv = reinterpret_cast<const float4*>(x)[o];
+  const float4 ev = reinterpret_cast<const float4*>(eps)[o];
   float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (z != nullptr) zv = reinterpret_cast<const float4*>(z)[i];
-  else if (seed != nullptr) zv = philox_normal4(*seed, stream, i);
-  float4 o;
-  o.x = post1(xv.x, ev.x, zv.x, k);
-  o.y = post1(xv.y, ev.y, zv.y, k);
-  o.z = post1(xv.z, ev.z, zv.z, k);
-  o.w = post1(xv.w, ev.w, zv.w, k);
-  reinterpret_cast<float4*>(out)[i] = o;
+  if (add_noise) {
+    if (z != nullptr) zv = reinterpret_cast<const float4*>(z)[o];
+    else if (args != nullptr) {
+      const float* nz = args->noise;
+      if (nz != nullptr) zv = reinterpret_cast<const float4*>(nz)[size_t(z_block) * gridDim.y * n4_img + o];
+      else zv = philox_normal4(args->seed, stream, args->image0 + blockIdx.y, i);
+    }
+  }
+  float4 r;
+  r.x = post1(xv.x, ev.x, zv.x, k);
+  r.y = post1(xv.y, ev.y, zv.y, k);
+  r.z = post1(xv.z, ev.z, zv.z, k);
+  r.w = post1(xv.w, ev.w, zv.w, k);
+  reinterpret_cast<float4*>(out)[o] = r;
 }
 
 // res2img (diffusion.py:275-281): clamp(x,-1,1)/2 + cond.  `out` rows may be strided per sample
-// so the same kernel fills the continous=True trace: out[b*out_bstride + i].
+// so the same kernel fills the continous=True trace: out[b*out_bstride + i]; out == nullptr: frame `frame_off`
+// (floats) of args->trace.  raw != 0: plain copy of x (the SR3 baseline's frames are the images themselves).
 __global__ void res2img_kernel(const float* __restrict__ x, const float* __restrict__ cond,
                                float* __restrict__ out, int64_t per_sample, int64_t out_bstride,
-                               int B) {
+                               int B, const SampleArgs* __restrict__ args, int64_t frame_off, int raw) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= per_sample * B) return;
+  float* o = out != nullptr ? out : args->trace + frame_off;
   const int64_t b = i / per_sample, r = i - b * per_sample;
   const float v = fminf(fmaxf(x[i], -1.0f), 1.0f);
-  out[b * out_bstride + r] = __fadd_rn(__fdiv_rn(v, 2.0f), cond[i]);
+  o[b * out_bstride + r] = raw ? x[i] : __fadd_rn(__fdiv_rn(v, 2.0f), cond[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -273,7 +300,8 @@ __global__ void slam_apply_kernel(const T* __restrict__ x, const float* __restri
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
       float t = 0.f;
       for (int w8 = 0; w8 < 8; ++w8) t += sacc[w8 * C + i];  // fixed order
-      atomicAdd(&stats[int64_t(b) * C + i], static_cast<unsigned long long>(__double2ll_rn(double(t) * kStatScale)));
+      atomicAdd(&stats[int64_t(b) * C + i],   // [pair][2]: even = sum, odd = sum of squares
+                static_cast<unsigned long long>(__double2ll_rn(double(t) * ((i & 1) ? kStatScaleSq : kStatScale))));
     }
 }
 

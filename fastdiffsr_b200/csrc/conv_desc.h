@@ -109,10 +109,13 @@ struct ConvLayer {
   int32_t out_mode;     // OutMode
   int32_t out_c;
   const uint8_t* weights;  // packed blobs
+  int32_t pair;            // 1: launched as CTA pairs (conv_gemm_kernel<.., kPair = true>): `weights` is the half-width
+  int32_t w_half;          //    layout, CTA r of a pair reads from weights + r * w_half
   int32_t phases;          // 1, or 4: tiles run over virtual images (image * 4 + phase), H/W are the low-resolution
                            // grid, every tap position is shifted by (py*kPatchW + px), weights are per phase
   int32_t tiles_x, tiles_y, ntiles;
   int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)
+  unsigned int* flags;     // context status word: bit 0 = an fp16 activation store saturated (overflow)
   int32_t dbg;             // experiments (tools/): bit0 skip epilogue work, bit1 skip producer work
   long long* prof;         // role cycle counters [grid][4 roles][8 slots] (FDSR_PROFILE builds only)
 };

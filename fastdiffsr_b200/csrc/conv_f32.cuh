@@ -68,7 +68,7 @@ __global__ void f32_gn_table_kernel(F32GnArgs a) {
     }
     const double n = double(cpg) * a.HW;
     const double mean = double(Si) * (1.0 / 16777216.0) / n;
-    double var = double(Qi) * (1.0 / 16777216.0) / n - mean * mean;
+    double var = double(Qi) * (1.0 / kStatScaleSq) / n - mean * mean;
     var = var > 0.0 ? var : 0.0;
     gs[threadIdx.x] = make_float2(float(mean), float(1.0 / sqrt(var + double(a.eps))));
   }
@@ -204,9 +204,9 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const __grid_constant__ F
     if (pg == 0 && nvalid) {
       unsigned long long* st = L.out_stats + size_t(b) * L.N + n;  // pair entries: (sum, sum of squares)
       atomicAdd(st + 0, static_cast<unsigned long long>(__double2ll_rn((double(s[0]) + double(s[1])) * 16777216.0)));
-      atomicAdd(st + 1, static_cast<unsigned long long>(__double2ll_rn((double(q[0]) + double(q[1])) * 16777216.0)));
+      atomicAdd(st + 1, static_cast<unsigned long long>(__double2ll_rn((double(q[0]) + double(q[1])) * kStatScaleSq)));
       atomicAdd(st + 2, static_cast<unsigned long long>(__double2ll_rn((double(s[2]) + double(s[3])) * 16777216.0)));
-      atomicAdd(st + 3, static_cast<unsigned long long>(__double2ll_rn((double(q[2]) + double(q[3])) * 16777216.0)));
+      atomicAdd(st + 3, static_cast<unsigned long long>(__double2ll_rn((double(q[2]) + double(q[3])) * kStatScaleSq)));
     }
   }
 }

@@ -45,6 +45,10 @@ constexpr int kMaxGnC = 512;
 // GroupNorm statistics are accumulated as 64-bit fixed point (2^-24 resolution): integer atomics
 // are associative, so the sums do not depend on the order in which CTAs finish.
 constexpr double kStatScale = 16777216.0;
+// sums of squares use 2^-16: per channel pair and image they reach 2 H W x^2, which at 2^-24 would wrap 63 bits once
+// the activation rms approaches 1e3 at 512^2 (possible in the bf16 mode with a trained network); 2^-16 holds
+// rms 1.6e4 at 512^2 and still resolves 1.5e-5 per tile partial sum
+constexpr double kStatScaleSq = 65536.0;
 
 template <int N>
 struct ConvCfg {
@@ -89,7 +93,8 @@ struct ConvCfg {
   static constexpr int kOffBias = kOffGstat + 64 * 8;
   static constexpr int kOffTstat = kOffBias + 256 * 4;
   static constexpr int kOffBar = kOffTstat + kEpiWarps * kRow * 4;  // one row of pair sums per epilogue warp
-  static constexpr int kNumBar = 3 * kASlots + 2 * kBStages + 2 * kNumAcc;
+  // (+ the pair-mode relay barriers: the peer CTA's a_full / b_full / acc_empty as seen by the leader's MMA warp)
+  static constexpr int kNumBar = 3 * kASlots + 2 * kBStages + 2 * kNumAcc + (kASlots + kBStages + kNumAcc);
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   // per-epilogue-warp 2 KB staging block for the TMA store of 32 px x 32 ch (64B-swizzled)
   static constexpr int kOffStage = ((kOffTmem + 16 + 1023) / 1024) * 1024;
@@ -108,6 +113,13 @@ struct Cvt<__half> {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   }
+  // activation store: saturate to +-65504 instead of producing inf (an inf becomes NaN in the next GroupNorm and
+  // silently corrupts the image); the epilogue also raises the context's overflow flag, see kOverflowCheck
+  __device__ static __forceinline__ uint32_t pack_store(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
 };
 template <>
 struct Cvt<__nv_bfloat16> {
@@ -119,6 +131,7 @@ struct Cvt<__nv_bfloat16> {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   }
+  __device__ static __forceinline__ uint32_t pack_store(float a, float b) { return pack(a, b); }  // fp32 exponent range
 };
 
 __device__ __forceinline__ float swish_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
@@ -132,28 +145,47 @@ __device__ __forceinline__ uint32_t swish_h2(uint32_t x, uint32_t sc, uint32_t s
   return o;
 }
 
-// GroupNorm scale/shift + Swish on 8 packed 16-bit activations.
-// kFast: packed fp16 (hsc/hsh hold scale/2, shift/2); otherwise fp32 EX2/RCP with sc/sh.
+// Operand format of a GroupNorm chunk.  fp16 mode: fp16.  bf16 mode: ALSO fp16 — activations are stored as bf16 (the
+// un-normalised residual stream of a trained network may exceed the fp16 range), but what a GroupNorm chunk feeds the
+// tensor core is swish(GroupNorm(x)), bounded by construction, so it is rounded to fp16 (11-bit significand instead of
+// 8) and multiplied with fp16 weights; raw chunks (1x1 residual conv, up / down-sampling convs, stem) stay bf16 x bf16.
+// tcgen05 kind::f16 takes the operand format per instruction.  This is what brings the bf16 mode inside the 1e-2
+// per-step tolerance (bf16 operand rounding alone costs 0.9e-2).
+template <typename T>
+using GnOperand = __half;
+
+// GroupNorm scale/shift + Swish on 8 packed 16-bit activations; the result is packed as GnOperand<T> (fp16).
+// kFast, fp16 storage: packed fp16 throughout (hsc/hsh hold scale/2, shift/2): swish(y) = h tanh(h) + h, h = y/2.
+// kFast, bf16 storage: the affine part in fp32 (sc/sh hold scale/2, shift/2; the input may be far outside the fp16
+//   range), then the same packed-half tanh form.
+// otherwise: fp32 EX2/RCP with sc/sh.
 template <typename T, bool kFast>
 __device__ __forceinline__ uint4 gn_swish_unit(uint4 o, const uint4& hsc, const uint4& hsh, const float (&sc)[8],
                                                const float (&sh)[8]) {
-  if (kFast) {
+  if constexpr (kFast && Cvt<T>::kFmt == 0) {
     o.x = swish_h2(o.x, hsc.x, hsh.x);
     o.y = swish_h2(o.y, hsc.y, hsh.y);
     o.z = swish_h2(o.z, hsc.z, hsh.z);
     o.w = swish_h2(o.w, hsc.w, hsh.w);
     return o;
-  }
-  const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
-  uint32_t r4[4];
+  } else {
+    const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+    uint32_t r4[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float2 f = Cvt<T>::unpack(w4[e]);
-    const float a = swish_f(fmaf(f.x, sc[2 * e], sh[2 * e]));
-    const float bb = swish_f(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
-    r4[e] = Cvt<T>::pack(a, bb);
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = Cvt<T>::unpack(w4[e]);
+      const float ya = fmaf(f.x, sc[2 * e], sh[2 * e]), yb = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+      if constexpr (kFast) {
+        const uint32_t h = Cvt<__half>::pack(ya, yb);  // = y/2 (pre-halved table)
+        uint32_t t;
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r4[e]) : "r"(h), "r"(t));
+      } else {
+        r4[e] = Cvt<GnOperand<T>>::pack(swish_f(ya), swish_f(yb));
+      }
+    }
+    return make_uint4(r4[0], r4[1], r4[2], r4[3]);
   }
-  return make_uint4(r4[0], r4[1], r4[2], r4[3]);
 }
 
 // GroupNorm scale/shift only (the SelfAttention norm of the SR3 baseline has no activation,
@@ -161,7 +193,7 @@ __device__ __forceinline__ uint4 gn_swish_unit(uint4 o, const uint4& hsc, const 
 template <typename T, bool kFast>
 __device__ __forceinline__ uint4 gn_affine_unit(uint4 o, const uint4& hsc, const uint4& hsh, const float (&sc)[8],
                                                 const float (&sh)[8]) {
-  if (kFast) {
+  if constexpr (kFast && Cvt<T>::kFmt == 0) {
     const uint32_t w4[4] = {o.x, o.y, o.z, o.w}, s4[4] = {hsc.x, hsc.y, hsc.z, hsc.w}, b4[4] = {hsh.x, hsh.y, hsh.z, hsh.w};
     uint32_t r4[4];
 #pragma unroll
@@ -174,10 +206,11 @@ __device__ __forceinline__ uint4 gn_affine_unit(uint4 o, const uint4& hsc, const
   }
   const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
   uint32_t r4[4];
+  const float k = (kFast && Cvt<T>::kFmt != 0) ? 2.0f : 1.0f;  // (bf16 fast table: scale/2, shift/2)
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float2 f = Cvt<T>::unpack(w4[e]);
-    r4[e] = Cvt<T>::pack(fmaf(f.x, sc[2 * e], sh[2 * e]), fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
+    r4[e] = Cvt<GnOperand<T>>::pack(k * fmaf(f.x, sc[2 * e], sh[2 * e]), k * fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]));
   }
   return make_uint4(r4[0], r4[1], r4[2], r4[3]);
 }
@@ -257,7 +290,17 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane)
 #endif
 
 // kFast: GroupNorm-affine + Swish in packed fp16 (tanh form); otherwise fp32 EX2/RCP.
-template <int N, typename T, bool kFast>
+// kPair: CTA-pair form.  The kernel runs as clusters of two CTAs (one per SM of a TPC) and every MMA is a
+//   tcgen05.mma.cta_group::2 of M = 256 rows: each CTA still owns a whole 32x8-pixel tile (its own input patch,
+//   producers, TMEM accumulators and epilogue) but stages only HALF of the weight columns — CTA r supplies columns
+//   [N/2 r, N/2 r + N/2) of B and the hardware exchanges the halves between the two SMs.  That halves both the weight
+//   bytes written into shared memory per tile and the B bytes the tensor core reads per MMA: this kernel is bound by the
+//   128 B/cycle of shared-memory bandwidth (an M128 x N64 x K16 MMA reads 4 KB of A + 2 KB of B for 32 cycles of math;
+//   as a pair 4 KB + 1 KB).  The two tiles of a pair are x-neighbours (tile 2k + r), so they share the virtual image /
+//   phase and therefore the weights.  Only the leader's warp 0 issues MMAs; the peer's warp 0 walks the same sequence
+//   and forwards "my patch stage / weight half / accumulator is ready" to relay barriers in the leader's shared memory;
+//   completions are multicast to both CTAs by tcgen05.commit.cta_group::2.
+template <int N, typename T, bool kFast, bool kPair>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   using Cfg = ConvCfg<N>;
@@ -283,36 +326,49 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   auto bar_raw_full = [&](int s) {  // TMA-fed layers: the raw patch of stage s has landed
     return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + 2 * Cfg::kNumAcc + s);
   };
+  // pair-mode relay barriers (used in the leader CTA only; arrivals come from the peer's warp 0)
+  constexpr int kBarRelay0 = 3 * kASlots + 2 * Cfg::kBStages + 2 * Cfg::kNumAcc;
+  auto bar_pa_full = [&](int s) { return bar0 + 8u * (kBarRelay0 + s); };
+  auto bar_pb_full = [&](int s) { return bar0 + 8u * (kBarRelay0 + kASlots + s); };
+  auto bar_pacc_empty = [&](int s) { return bar0 + 8u * (kBarRelay0 + kASlots + Cfg::kBStages + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
-  // Optional thread-block cluster of 2 CTAs (FDSR_CLUSTER=1): the CTAs walk the same layer in lock
-  // step and share every weight stage — each loads half of it and multicasts it to both, halving
-  // the L2 -> SM weight traffic.  Measured on B200: correct, but no speed-up for this kernel (L2
-  // bandwidth is not its limiter), so it is off by default.
-  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
-  const uint16_t cmask = uint16_t((1u << csize) - 1u);
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
+  constexpr int NB = kPair ? N / 2 : N;                    // weight columns this CTA stages
+  constexpr int kTStep = kPair ? 2 : 1;                    // a CTA of a pair walks every second tile
 
   if (tid == 0) {
     for (int s = 0; s < kASlots; ++s) {
       mbar_init(bar_a_full(s), kProdWarps);
       mbar_init(bar_a_empty(s), 1);
       mbar_init(bar_raw_full(s), 1);
+      mbar_init(bar_pa_full(s), 1);
     }
     for (int s = 0; s < Cfg::kBStages; ++s) {
       mbar_init(bar_b_full(s), 1);
-      mbar_init(bar_b_empty(s), csize);  // released by the MMA warp of every CTA in the cluster
+      mbar_init(bar_b_empty(s), 1);
+      mbar_init(bar_pb_full(s), 1);
     }
     for (int s = 0; s < Cfg::kNumAcc; ++s) {
       mbar_init(bar_acc_full(s), 1);
       mbar_init(bar_acc_empty(s), kEpiWarps);
+      mbar_init(bar_pacc_empty(s), 1);
     }
     mbar_init_fence();
   }
-  if (warp == 0) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
+  if (warp == 0) tmem_alloc<Cfg::kTmemCols, kPair>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // every CTA's barriers exist before any remote arrive / copy
+  if (kPair) cluster_sync_all();  // both CTAs' barriers and TMEM exist before any remote arrive / pair MMA
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (kPair && tid == 0) {
+    // the pair MMA writes the same TMEM address in both CTAs: the two allocations must agree (they do: one CTA per
+    // SM, one allocation per CTA); a mismatch would corrupt results silently, so fail loudly instead
+    uint32_t ra, other;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(tmem_slot)), "r"(crank ^ 1u));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(other) : "r"(ra) : "memory");
+    if (other != tmem) asm volatile("trap;");
+  }
   // Programmatic dependent launch: the next layer's CTAs may become resident (and run the prologue
   // above) as soon as SMs drain; everything that reads or writes activations / statistics waits here
   // for the previous launch to complete.  The weight loader (warp 1) only touches constant data.
@@ -324,26 +380,26 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   // The unit of assignment is a group of L.group consecutive tiles of one image: running statistics
   // are reduced per group, so every partial sum is computed identically whatever the batch size or
   // the position of the image in the batch (results are bitwise independent of how a batch is sharded).
+  // Pair mode: the unit of work is a PAIR of x-neighbouring tiles (2k, 2k + 1) — tiles_x is even — of which CTA r
+  // computes tile 2k + r; [tile_begin, tile_end) then counts pairs and the CTA walks every second tile.
   const int tgroup = L.group;
-  const int ngroups = L.ntiles / tgroup;
-  // clusters take contiguous runs of `csize` groups ("units"); inside a cluster every CTA gets the
-  // same number of groups, so all CTAs of a cluster consume weight stages at the same cadence
+  const int ngroups = (L.ntiles / kTStep) / tgroup;
   // Split-N (L.nsplit > 1, low-resolution layers whose tile count would leave most SMs idle): CTA
   // `part` computes output channels [part*N, part*N + N) of the n_full-wide layer for its tiles.
   const int nsplit = L.nsplit;
-  const int part = int(blockIdx.x) % nsplit;  // (split-N layers are never clustered)
+  const int part = int(blockIdx.x) % nsplit;  // (split-N layers are never paired)
   const int n_off = part * N, n_full = L.n_full;
-  const int nclusters = int(gridDim.x / csize) / nsplit, cid = int(blockIdx.x / csize) / nsplit;
-  const int nunits = ngroups / int(csize);
-  const int tq = nunits / nclusters, tr = nunits - tq * nclusters;
+  const int nclusters = int(gridDim.x / kTStep) / nsplit, cid = int(blockIdx.x / kTStep) / nsplit;
+  const int tq = ngroups / nclusters, tr = ngroups - tq * nclusters;
   const int unit_begin = cid * tq + (cid < tr ? cid : tr);
   const int my_units = tq + (cid < tr ? 1 : 0);
-  const int tile_begin = (unit_begin * int(csize) + int(crank) * my_units) * tgroup;
+  const int tile_begin = unit_begin * tgroup;
   const int tile_end = tile_begin + my_units * tgroup;
+  const int tile_first = tile_begin * kTStep + int(crank);  // index of this CTA's first tile in the layer's tile order
   const int tiles_per_img = L.tiles_x * L.tiles_y;
   const int ncg = L.ncg;
-  const uint32_t blob = uint32_t(ncg) * N * 16;  // bytes of one tap's weight blob (this CTA's N columns)
-  const uint32_t gblob = uint32_t(ncg) * uint32_t(n_full) * 16;  // the same tap in global memory (all columns)
+  const uint32_t blob = uint32_t(ncg) * NB * 16;  // bytes of one tap's weight blob (the columns this CTA stages)
+  const uint32_t gblob = uint32_t(ncg) * uint32_t(n_full) * 16;  // split-N: the same tap in global memory (all columns)
   const int taps_per_stage =
       int(Cfg::kBStageBytes / blob) < kMaxTaps ? int(Cfg::kBStageBytes / blob) : kMaxTaps;
   const uint32_t sA = smem_u32(smem + Cfg::kOffA);
@@ -357,7 +413,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   if (warp == 0) {
     // =========================================================== MMA issuer (whole warp converged,
     // tcgen05 instructions issued by the elected lane)
-    const uint32_t idesc = make_idesc_f16(128, N, Cvt<T>::kFmt);
+    const uint32_t idesc_raw = make_idesc_f16(kPair ? 256 : 128, N, Cvt<T>::kFmt);
+    const uint32_t idesc_gn = make_idesc_f16(kPair ? 256 : 128, N, Cvt<GnOperand<T>>::kFmt);  // (see GnOperand)
+    const bool leader = crank == 0;  // (pair mode: the peer's warp 0 only forwards its barriers to the leader)
     // descriptor = hi:lo; hi is constant, lo = (LBO>>4)<<16 | (addr>>4), advanced by plain adds
     // A operand: no-swizzle channel-group planes (SBO = 10 positions x 16 B, LBO = plane) when the
     // producers gather it, 128B-swizzled pixel-major rows (SBO = 10 positions x 128 B, layout type 2)
@@ -372,7 +430,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const uint32_t kstep = sw ? 2u : 2u * kPlanePos;  // 16-byte units between K = 16 slices
     const int pos_sh = sw ? 3 : 0;                    // patch position -> 16-byte units
     const uint32_t mt1_full = uint32_t(16 * kPatchW) << pos_sh;  // second 128-row MMA tile: 16 image rows down
-    const uint32_t b_lo0 = (uint32_t((N * 16) >> 4) << 16) + ((sB & 0x3FFFFu) >> 4);
+    const uint32_t b_lo0 = (uint32_t((NB * 16) >> 4) << 16) + ((sB & 0x3FFFFu) >> 4);
     const int ksteps = ncg >> 1;
     int gs = 0, gph = 0, rs = 0, rph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
     // Weight stages hold taps_per_stage consecutive taps of the CTA's whole tap stream (all chunks of a
@@ -381,21 +439,35 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     int bq = 0;
     // phase layers (L.phases = 4): tiles run over virtual images bv = image * 4 + (py * 2 + px); the 2x2 taps of
     // phase (py, px) are the phase-0 taps shifted by (py, px) positions inside the low-resolution patch
-    int m_bv = tile_begin / tiles_per_img, m_tin = tile_begin - m_bv * tiles_per_img;
+    int m_bv = tile_first / tiles_per_img, m_tin = tile_first - m_bv * tiles_per_img;
+    // Pair mode hand-shake.  A barrier the MMA warp waits for exists in both CTAs (each CTA's producers, loader and
+    // epilogue only ever talk to their own); the peer's warp 0 waits for its local one and then arrives on the relay
+    // barrier of the same stage in the leader's shared memory, which the leader waits for after its own.  The k-th use
+    // of a stage completes phase k-1 of its relay barrier (also for acc_empty, whose first local wait falls through).
+    auto pair_sync = [&](uint32_t relay_bar, uint32_t use_parity) {
+      if constexpr (kPair) {
+        if (leader) mbar_wait(relay_bar, use_parity);
+        else if (lane == 0) mbar_arrive_remote(relay_bar, 0);
+        __syncwarp();
+      }
+    };
     PROF_DECL;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(bar_acc_empty(acc), accph ^ 1);
+      pair_sync(bar_pacc_empty(acc), accph);
       PROF_MARK(0);
       tc_fence_after();
       const uint32_t d0 = tmem + acc * Cfg::kAccCols;
       const uint32_t phoff = L.phases > 1 ? uint32_t(((m_bv >> 1) & 1) * kPatchW + (m_bv & 1)) << pos_sh : 0u;
-      if (++m_tin == tiles_per_img) { m_tin = 0; ++m_bv; }
+      if ((m_tin += kTStep) >= tiles_per_img) { m_tin -= tiles_per_img; ++m_bv; }
       for (int c = 0; c < L.nchunks; ++c) {
         const ConvChunk& ck = L.chunk[c];
         const int ntaps = ck.ntaps;
         const bool r1 = ck.ring != 0;
         const int as = r1 ? nG + rs : gs;
+        const uint32_t idesc = ck.gn != 0 ? idesc_gn : idesc_raw;
         mbar_wait(bar_a_full(as), r1 ? rph : gph);
+        pair_sync(bar_pa_full(as), r1 ? rph : gph);
         PROF_MARK(1);
         const uint32_t a_stage = a_lo0 + (slot_off(as) >> 4);
         // centre-box chunk (raw single-tap chunk of a TMA-fed layer): dense 32x8 positions, no halo
@@ -404,40 +476,44 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         const uint32_t mt1 = cen ? uint32_t(16 * kTileW) << 3 : mt1_full;
         for (int tp0 = 0; tp0 < ntaps;) {
           const int g = ntaps - tp0 < taps_per_stage - bq ? ntaps - tp0 : taps_per_stage - bq;
-          if (bq == 0) mbar_wait(bar_b_full(bs), bph);
+          if (bq == 0) {
+            mbar_wait(bar_b_full(bs), bph);
+            pair_sync(bar_pb_full(bs), bph);
+          }
           PROF_MARK(2);
           tc_fence_after();
           const bool stage_done = bq + g == taps_per_stage;
-          if (elect_one()) {
+          if (leader && elect_one()) {
             uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4) + bq * (blob >> 4);
             for (int tg = 0; tg < g; ++tg, b_lo += blob >> 4) {
               const uint32_t a_lo = a_stage + (cen ? 0u : (uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh) + phoff);
               const uint32_t accum0 = (c | tp0 | tg) == 0 ? 0u : 1u;
+              auto issue = [&](int ks) {
+                const uint64_t bd = (uint64_t(b_hi) << 32) | (b_lo + ks * 2 * NB);
+                const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep);
+                const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep + mt1);
+                if constexpr (kPair) {
+                  umma_f16_pair(d0, ad0, bd, idesc, ks ? 1u : accum0);
+                  umma_f16_pair(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
+                } else {
+                  umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
+                  umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
+                }
+              };
               if (ksteps == 4) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t bd = (uint64_t(b_hi) << 32) | (b_lo + ks * 2 * N);
-                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep);
-                  const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep + mt1);
-                  umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
-                  umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
-                }
+                for (int ks = 0; ks < 4; ++ks) issue(ks);
               } else {
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  const uint64_t bd = (uint64_t(b_hi) << 32) | (b_lo + ks * 2 * N);
-                  const uint64_t ad0 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep);
-                  const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep + mt1);
-                  umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
-                  umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
-                }
+                for (int ks = 0; ks < ksteps; ++ks) issue(ks);
               }
             }
-            if (stage_done) {  // (the last, partial stage of the CTA is never waited for)
-              if (csize > 1) umma_commit_multicast(bar_b_empty(bs), cmask);
-              else umma_commit(bar_b_empty(bs));
-            }
-            if (tp0 + g >= ntaps) umma_commit(bar_a_empty(as));
-            if (tp0 + g >= ntaps && c == L.nchunks - 1) umma_commit(bar_acc_full(acc));
+            auto commit = [&](uint32_t bar) {
+              if constexpr (kPair) umma_commit_pair(bar);
+              else umma_commit(bar);
+            };
+            if (stage_done) commit(bar_b_empty(bs));  // (the last, partial stage of the CTA is never waited for)
+            if (tp0 + g >= ntaps) commit(bar_a_empty(as));
+            if (tp0 + g >= ntaps && c == L.nchunks - 1) commit(bar_acc_full(acc));
           }
           __syncwarp();
           PROF_MARK(3);
@@ -471,10 +547,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const int total = (tile_end - tile_begin) * L.nchunks;
     // patch cursor
     int a_next = tma_in ? 0 : total, a_c = 0, a_gs = 0, a_gph = 0, a_rs = 0, a_rph = 0;
-    int a_b = tile_begin / tiles_per_img;
+    int a_b = tile_first / tiles_per_img;
     int a_ty, a_tx;
     {
-      const int rem = tile_begin - a_b * tiles_per_img;
+      const int rem = tile_first - a_b * tiles_per_img;
       a_ty = rem / L.tiles_x;
       a_tx = rem - a_ty * L.tiles_x;
     }
@@ -484,13 +560,14 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     for (int c = 0; c < L.nchunks; ++c) taps_tile += L.chunk[c].ntaps;
     const int total_taps = (tile_end - tile_begin) * taps_tile;
     int b_q = 0, b_qq = 0, bs = 0, bph = 0;  // next tap overall / inside its tile
-    const uint8_t* const w0 = L.weights + size_t(n_off) * 16;
+    // (pair mode: the weights are packed as two half-width copies of the single-CTA layout, half r for CTA r)
+    const uint8_t* const w0 = L.weights + (kPair ? size_t(crank) * size_t(L.w_half) : size_t(n_off) * 16);
     int b_issued = 0;
     // phase layers: the weights of phase p follow those of phase p-1 (taps_tile blobs each); w_bv / w_tin = virtual
     // image / tile-in-image of the tile that tap b_q belongs to
     const int phsh = L.phases > 1 ? 2 : 0;
-    const size_t ph_stride = L.phases > 1 ? size_t(taps_tile) * gblob : 0;
-    int w_bv = tile_begin / tiles_per_img, w_tin = tile_begin - w_bv * tiles_per_img;
+    const size_t ph_stride = L.phases > 1 ? size_t(taps_tile) * (kPair ? blob : gblob) : 0;
+    int w_bv = tile_first / tiles_per_img, w_tin = tile_first - w_bv * tiles_per_img;
     while (a_next < total || b_q < total_taps) {
       bool progress = false;
       if (!dep_ok && (b_issued >= Cfg::kBStages || b_q >= total_taps)) {
@@ -533,8 +610,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           }
           if (++a_c == L.nchunks) {
             a_c = 0;
-            if (++a_tx == L.tiles_x) {
-              a_tx = 0;
+            if ((a_tx += kTStep) >= L.tiles_x) {
+              a_tx -= L.tiles_x;
               if (++a_ty == L.tiles_y) { a_ty = 0; ++a_b; }
             }
           }
@@ -546,9 +623,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         if (__shfl_sync(0xffffffffu, ok, 0)) {
           const int g = total_taps - b_q < taps_per_stage ? total_taps - b_q : taps_per_stage;
           if (elect_one()) {
-            mbar_arrive_expect_tx(bar_b_full(bs), uint32_t(g) * blob);  // own slices + the peers' multicast slices
+            mbar_arrive_expect_tx(bar_b_full(bs), uint32_t(g) * blob);
             const uint32_t dst0 = sB + bs * Cfg::kBStageBytes;
-            if (csize == 1 && nsplit == 1) {
+            if (nsplit == 1) {
               // contiguous runs up to the end of each tile's taps (the next tile may belong to another phase)
               int rem = g, qq = b_qq, tin = w_tin, bv = w_bv;
               uint32_t dst = dst0;
@@ -560,7 +637,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                 qq += n;
                 if (qq == taps_tile) {
                   qq = 0;
-                  if (++tin == tiles_per_img) { tin = 0; ++bv; }
+                  if ((tin += kTStep) >= tiles_per_img) { tin -= tiles_per_img; ++bv; }
                 }
               }
             } else {
@@ -568,14 +645,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               for (int tg = 0; tg < g; ++tg) {
                 const uint8_t* wt = w0 + size_t(bv & 3) * ph_stride + size_t(qq) * gblob;
                 const uint32_t dst = dst0 + uint32_t(tg) * blob;
-                if (csize > 1) {
-                  const uint32_t slice = blob / csize;
-                  bulk_g2s_multicast(dst + crank * slice, wt + crank * slice, slice, bar_b_full(bs), cmask);
-                } else {
-                  // this CTA's N of the n_full columns: one contiguous run per channel group
-                  for (int cgi = 0; cgi < ncg; ++cgi)
-                    bulk_g2s(dst + uint32_t(cgi) * N * 16, wt + size_t(cgi) * n_full * 16, N * 16, bar_b_full(bs));
-                }
+                // this CTA's N of the n_full columns: one contiguous run per channel group
+                for (int cgi = 0; cgi < ncg; ++cgi)
+                  bulk_g2s(dst + uint32_t(cgi) * N * 16, wt + size_t(cgi) * n_full * 16, N * 16, bar_b_full(bs));
                 if (++qq == taps_tile) {
                   qq = 0;
                   if (++tin == tiles_per_img) { tin = 0; ++bv; }
@@ -587,7 +659,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
           b_q += g;
           for (b_qq += g; b_qq >= taps_tile; b_qq -= taps_tile)
-            if (++w_tin == tiles_per_img) { w_tin = 0; ++w_bv; }
+            if ((w_tin += kTStep) >= tiles_per_img) { w_tin -= tiles_per_img; ++w_bv; }
           ++b_issued;
           progress = true;
         }
@@ -622,9 +694,13 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       tmem_st_wait();
     }
     int acc = 0, accph = 0;
-    int b = tile_begin / tiles_per_img;
-    int rem = tile_begin - b * tiles_per_img;
+    int b = tile_first / tiles_per_img;
+    int rem = tile_first - b * tiles_per_img;
     int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    // fp16 storage: values beyond +-65504 are stored saturated AND reported through the context's overflow flag, so that
+    // the host can fail loudly / re-run in the bf16 mode instead of returning a silently clipped image
+    constexpr bool kOverflowCheck = Cvt<T>::kFmt == 0;
+    float vmax = 0.f;
     PROF_DECL;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int x = tx * kTileW + r, y = ty * kTileH + mt * 16 + g;
@@ -644,9 +720,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + k, valid);
         // pull this lane's residual row of the NEXT tile into L2 while this tile is drained (the loads
         // above then mostly hit L2 instead of exposing HBM latency on the epilogue's critical path)
-        int ntx = tx + 1, nty = ty, nb = b;
-        if (ntx == tiles_x) {
-          ntx = 0;
+        int ntx = tx + kTStep, nty = ty, nb = b;
+        if (ntx >= tiles_x) {
+          ntx -= tiles_x;
           if (++nty == L.tiles_y) { nty = 0; ++nb; }
         }
         const int nx = ntx * kTileW + r, ny = nty * kTileH + mt * 16 + g;
@@ -693,6 +769,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + (cb + 1) * 4 + k, valid);
             }
           }
+          if constexpr (kOverflowCheck) {  // largest magnitude about to be stored as fp16 (one FMNMX3 per two values)
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) vmax = fmaxf(vmax, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+          }
           if (use_tma && !(L.dbg & 4)) {
             // stage the warp's 32 px x 32 ch block (64B-swizzled rows), then one bulk tensor store:
             // full 64-byte segments per pixel instead of 32 scattered 16-byte writes per instruction
@@ -702,8 +782,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             for (int k = 0; k < 4; ++k) {
               const uint32_t dst = stage_s + uint32_t(lane) * 64 + uint32_t((k ^ ((lane >> 1) & 3)) * 16);
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst),
-                           "r"(Cvt<T>::pack(v[k * 8 + 0], v[k * 8 + 1])), "r"(Cvt<T>::pack(v[k * 8 + 2], v[k * 8 + 3])),
-                           "r"(Cvt<T>::pack(v[k * 8 + 4], v[k * 8 + 5])), "r"(Cvt<T>::pack(v[k * 8 + 6], v[k * 8 + 7]))
+                           "r"(Cvt<T>::pack_store(v[k * 8 + 0], v[k * 8 + 1])), "r"(Cvt<T>::pack_store(v[k * 8 + 2], v[k * 8 + 3])),
+                           "r"(Cvt<T>::pack_store(v[k * 8 + 4], v[k * 8 + 5])), "r"(Cvt<T>::pack_store(v[k * 8 + 6], v[k * 8 + 7]))
                            : "memory");
             }
             fence_proxy_async_smem();
@@ -718,10 +798,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               uint4 u;
-              u.x = Cvt<T>::pack(v[k * 8 + 0], v[k * 8 + 1]);
-              u.y = Cvt<T>::pack(v[k * 8 + 2], v[k * 8 + 3]);
-              u.z = Cvt<T>::pack(v[k * 8 + 4], v[k * 8 + 5]);
-              u.w = Cvt<T>::pack(v[k * 8 + 6], v[k * 8 + 7]);
+              u.x = Cvt<T>::pack_store(v[k * 8 + 0], v[k * 8 + 1]);
+              u.y = Cvt<T>::pack_store(v[k * 8 + 2], v[k * 8 + 3]);
+              u.z = Cvt<T>::pack_store(v[k * 8 + 4], v[k * 8 + 5]);
+              u.w = Cvt<T>::pack_store(v[k * 8 + 6], v[k * 8 + 7]);
               op[k] = u;
             }
           }
@@ -816,8 +896,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
       // next tile coordinates (no divisions in the loop)
       const int b_cur = b_img;
-      if (++tx == tiles_x) {
-        tx = 0;
+      if ((tx += kTStep) >= tiles_x) {
+        tx -= tiles_x;
         if (++ty == L.tiles_y) { ty = 0; ++b; }
       }
       if (do_stats && !(L.dbg & 1)) {
@@ -847,14 +927,16 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             float tsum = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += tstat[w8 * kRow + i];
+            // entry layout [pair][2]: even = sum, odd = sum of squares
             atomicAdd(L.out_stats + size_t(b_cur) * n_full + n_off + i,
-                      static_cast<unsigned long long>(__float2ll_rn(tsum * float(kStatScale))));
+                      static_cast<unsigned long long>(__float2ll_rn(tsum * float((i & 1) ? kStatScaleSq : kStatScale))));
           }
           named_bar_sync(2, kEpiThreads);
         }
       }
       PROF_MARK(2);
     }
+    if (kOverflowCheck && vmax > 65504.f && L.flags != nullptr) atomicOr(L.flags, 1u);
     if (lane == 0) bulk_wait_all0();  // outstanding bulk tensor stores of this warp
     if (et == 0) PROF_FLUSH(1);
   } else {
@@ -864,8 +946,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const int H = L.H, W = L.W, mode = L.mode, tiles_x = L.tiles_x;
     __half* table_h = reinterpret_cast<__half*>(table);
     int as = 0, aph = 0, cur_b = -1;
-    int b = tile_begin / tiles_per_img;
-    int rem = tile_begin - b * tiles_per_img;
+    int b = tile_first / tiles_per_img;
+    int rem = tile_first - b * tiles_per_img;
     int ty = rem / tiles_x, tx = rem - ty * tiles_x;
     PROF_DECL;
 
@@ -903,7 +985,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         }
         const double n = double(cpg) * L.src[0].H * L.src[0].W;
         const double mean = double(Si) * (1.0 / kStatScale) / n;
-        double var = double(Qi) * (1.0 / kStatScale) / n - mean * mean;
+        double var = double(Qi) * (1.0 / kStatScaleSq) / n - mean * mean;
         var = var > 0.0 ? var : 0.0;
         gstat[pidx] = make_float2(float(mean), float(1.0 / sqrt(var + double(L.gn_eps))));
       }
@@ -915,9 +997,11 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           const float2 gs = gstat[c / cpg];
           const float sc = ga[j] * gs.y;
           const float sh = be[j] - gs.x * sc;
-          if (kFast) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
+          if constexpr (kFast && Cvt<T>::kFmt == 0) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
             table_h[c] = __float2half_rn(0.5f * sc);
             table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
+          } else if constexpr (kFast) {  // bf16 storage: fp32 affine, then the packed-half tanh form
+            table[c] = make_float2(0.5f * sc, 0.5f * sh);
           } else {
             table[c] = make_float2(sc, sh);
           }
@@ -965,7 +1049,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             const int cgs = (pidx & 7) ^ ((pos0 + 5 * as) & 7);
             float sc[8], sh[8];
             uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
-            if (kFast) {
+            if constexpr (kFast && Cvt<T>::kFmt == 0) {
               hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cgs * 8);
               hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cgs * 8);
             } else {
@@ -997,8 +1081,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (lane == 0) mbar_arrive(bar_a_full(as));
           if (++as == nG) as = 0;
         }
-        if (++tx == tiles_x) {
-          tx = 0;
+        if ((tx += kTStep) >= tiles_x) {
+          tx -= tiles_x;
           if (++ty == L.tiles_y) { ty = 0; ++b; }
         }
       }
@@ -1073,7 +1157,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           float sc[8], sh[8];
           uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
           if (gn) {
-            if (kFast) {
+            if constexpr (kFast && Cvt<T>::kFmt == 0) {
               hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cg * 8);
               hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cg * 8);
             } else {
@@ -1104,8 +1188,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           PROF_MARK(3);
           if (++as == kAStages) { as = 0; aph ^= 1; }
         }
-        if (++tx == tiles_x) {
-          tx = 0;
+        if ((tx += kTStep) >= tiles_x) {
+          tx -= tiles_x;
           if (++ty == L.tiles_y) { ty = 0; ++b; }
         }
       }
@@ -1115,8 +1199,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
 
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it
-  if (warp == 0) tmem_dealloc<Cfg::kTmemCols>(tmem);
+  if (kPair) cluster_sync_all();  // neither CTA frees its TMEM / exits while the pair's MMAs or commits may still touch it
+  if (warp == 0) tmem_dealloc<Cfg::kTmemCols, kPair>(tmem);
 }
 
 }  // namespace fdsr

@@ -122,38 +122,37 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics
+// (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) uses for its 2-SM pipelines: the cluster-scope
+// form compiles to MEMBAR.ALL.GPU + CCTL.IVALL on every hand-off.  What the remote waiter consumes is shared memory
+// read by the async proxy (tcgen05.mma); its writers made it visible with fence.proxy.async before their own arrive.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
       "r"(rank)
-      : "memory");
-}
-// bulk copy global -> the same shared-memory offset of every CTA in `mask`; each destination CTA's
-// mbarrier (same offset) receives complete_tx for the bytes
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes,
-                                                   uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          dst_smem),
-      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
       : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
-template <int NCOLS>
+// kPair: the allocation of a CTA pair (cta_group::2) — one warp of EACH CTA of the pair executes it
+template <int NCOLS, bool kPair = false>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "n"(NCOLS)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (kPair) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
 }
-template <int NCOLS>
+template <int NCOLS, bool kPair = false>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS)
-               : "memory");
+  if constexpr (kPair)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -168,6 +167,18 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// CTA-pair form (cta_group::2), issued by one thread of the pair's leader CTA (cluster rank 0): M = 256 rows, CTA r
+// supplies rows [128 r, 128 r + 128) of A and columns [N/2 r, N/2 r + N/2) of B from the SAME shared-memory offsets
+// (the descriptors are CTA-relative) and receives its 128 rows x N columns of D in its own TMEM.
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -199,11 +210,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
       : "memory");
 }
-// same, arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+// completion of the pair's cta_group::2 MMAs: arrives on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"(mask)
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(uint16_t(3))
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {

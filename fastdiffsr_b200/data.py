@@ -49,17 +49,55 @@ def u8_to_tensor(img_u8: torch.Tensor):
     return (img_u8.permute(0, 3, 1, 2).float() / 255.0) * 2.0 - 1.0
 
 
+def _decode_rgb_u8(buf):
+    from io import BytesIO
+    from PIL import Image
+    with Image.open(BytesIO(buf)) as im:
+        return np.array(im.convert("RGB"), dtype=np.uint8)
+
+
+class _LmdbStore:
+    """Read-only view of an LMDB environment written by the reference's data/prepare_data_mfe_dm.py (keys
+    `hr_{r}_{idx:05d}`, `sr_{l}_{r}_{idx:05d}`, `lr_{l}_{idx:05d}`, `length`), opened exactly as
+    data/LRHR_dataset.py:17-19 does.  Needs the `lmdb` package, like the reference."""
+
+    def __init__(self, dataroot):
+        try:
+            import lmdb
+        except ImportError as e:
+            raise ImportError("datatype 'lmdb' needs the `lmdb` package (the reference imports it too, "
+                              "data/LRHR_dataset.py:2); install it or export the dataset to image folders") from e
+        self.env = lmdb.open(dataroot, readonly=True, lock=False, readahead=False, meminit=False)
+
+    def get(self, key: bytes):
+        with self.env.begin(write=False) as txn:
+            v = txn.get(key)
+            return None if v is None else bytes(v)
+
+
 class LRHRDataset:
-    """Folder layout of the reference: `{dataroot}/hr_{r}`, `{dataroot}/lr_{l}`, optional `{dataroot}/sr_{l}_{r}`."""
+    """The reference's validation dataset (data/LRHR_dataset.py:9-128): datatype 'img' = folder layout
+    `{dataroot}/hr_{r}`, `{dataroot}/lr_{l}`, optional `{dataroot}/sr_{l}_{r}`; datatype 'lmdb' = the key-value layout
+    of data/LRHR_dataset.py:17-27, 60-93 (`kv`: any object with get(key: bytes) -> bytes | None; default: the LMDB
+    environment at `dataroot`)."""
 
     def __init__(self, dataroot, datatype="img", l_resolution=64, r_resolution=256, split="val", data_len=-1,
-                 need_LR=True, img_mask="no"):
-        if datatype != "img":
-            raise NotImplementedError("data_type [{:s}] is not recognized (lmdb datasets are a training-side "
-                                      "format of the reference; convert to image folders)".format(str(datatype)))
+                 need_LR=True, img_mask="no", kv=None):
+        if datatype not in ("img", "lmdb"):
+            raise NotImplementedError('data_type [{:s}] is not recognized.'.format(str(datatype)))
         if split == "train":
-            raise NotImplementedError("the training data path (random flips, lmdb) is outside the B200 sampling path")
+            raise NotImplementedError("the training data path (random flips) is outside the B200 sampling path")
         self.l_res, self.r_res, self.split = l_resolution, r_resolution, split
+        self.datatype = datatype
+        self.need_LR = need_LR
+        if datatype == "lmdb":
+            self.kv = kv if kv is not None else _LmdbStore(dataroot)
+            length = self.kv.get("length".encode("utf-8"))
+            if length is None:
+                raise ValueError(f"{dataroot}: no 'length' key — not a dataset written by prepare_data_mfe_dm.py")
+            self.dataset_len = int(length)
+            self.data_len = self.dataset_len if (data_len is None or data_len <= 0) else min(data_len, self.dataset_len)
+            return
         self.hr_path = get_paths_from_images('{}/hr_{}'.format(dataroot, r_resolution))
         sr_dir = '{}/sr_{}_{}'.format(dataroot, l_resolution, r_resolution)
         lr_dir = '{}/lr_{}'.format(dataroot, l_resolution)
@@ -76,8 +114,24 @@ class LRHRDataset:
     def __len__(self):
         return self.data_len
 
+    def _lmdb_u8(self, index):
+        tag = str(index).zfill(5)
+        keys = {"HR": 'hr_{}_{}'.format(self.r_res, tag), "SR": 'sr_{}_{}_{}'.format(self.l_res, self.r_res, tag),
+                "LR": 'lr_{}_{}'.format(self.l_res, tag)}
+        raw = {k: self.kv.get(v.encode("utf-8")) for k, v in keys.items() if k != "LR" or self.need_LR}
+        # The reference replaces an invalid index by a RANDOM valid one (data/LRHR_dataset.py:77-92), which silently
+        # evaluates some image twice; validation here must be reproducible, so a hole in the store is an error
+        if raw["HR"] is None or (raw["SR"] is None and raw.get("LR") is None):
+            raise KeyError(f"lmdb dataset: index {index} has no {keys['HR']} / {keys['SR']} entry")
+        item = {k: _decode_rgb_u8(v) for k, v in raw.items() if v is not None}
+        item["Index"] = index
+        item["path"] = keys["HR"]
+        return item
+
     def get_u8(self, index):
         """uint8 HWC arrays: always 'HR'; 'LR' and/or 'SR' as present on disk."""
+        if self.datatype == "lmdb":
+            return self._lmdb_u8(index)
         item = {"HR": _load_rgb_u8(self.hr_path[index]), "Index": index, "path": self.hr_path[index]}
         if self.lr_path is not None:
             item["LR"] = _load_rgb_u8(self.lr_path[index])

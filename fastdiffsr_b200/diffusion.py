@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from .engine import Engine
-from ._lib import FdsrError
+from ._lib import FdsrError, FdsrOverflowError
 
 
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
@@ -73,7 +73,11 @@ class GaussianDiffusion(nn.Module):
         self.denoise_fn = denoise_fn
         self.loss_type = loss_type
         self.conditional = conditional
-        self.compute_dtype = dtype
+        # "fp16" | "bf16" | "fp32" | "auto".  "auto" samples in fp16 (highest accuracy at the same speed) and, should an
+        # activation leave the fp16 range (possible with a trained network's un-normalised residual stream), switches
+        # this netG to bf16 storage for good and repeats the call; "fp16" raises FdsrOverflowError in that case.
+        self.auto_dtype = dtype == "auto"
+        self.compute_dtype = "fp16" if self.auto_dtype else dtype
         self.sr3 = getattr(denoise_fn, "cfg", {}).get("model") == "ddpm"
         self._engine = None
         self._weights_dirty = True
@@ -169,21 +173,39 @@ class GaussianDiffusion(nn.Module):
         return eng.posterior_step(x, eps, z, int(t))
 
     @torch.no_grad()
-    def p_sample_loop(self, x_in, continous=False, noise=None, seed=None):
+    def p_sample_loop(self, x_in, continous=False, noise=None, seed=None, image_offset=0):
         if not self.conditional:
             raise NotImplementedError("unconditional sampling is not on the SR path (unused by every config)")
-        eng = self.engine()
-        if seed is None:
+        if seed is None:   # unseeded like the reference; ranks seeded alike must still draw different noise
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                seed = (seed + 0x9E3779B97F4A7C15 * torch.distributed.get_rank()) % (2 ** 63)
+        try:
+            return self._sample_checked(x_in, continous, noise, seed, image_offset)
+        except FdsrOverflowError:
+            if not self.auto_dtype:
+                raise
+            import warnings
+            warnings.warn("fastdiffsr_b200: an activation left the fp16 range; switching this network to the bf16 mode")
+            self.compute_dtype = "bf16"
+            self._engine.close()
+            self._engine = None
+            return self._sample_checked(x_in, continous, noise, seed, image_offset)
+
+    def _sample_checked(self, x_in, continous, noise, seed, image_offset):
+        eng = self.engine()
         if not continous:
-            sr = eng.sample(x_in, noise=noise, seed=seed)
+            sr = eng.sample(x_in, noise=noise, seed=seed, image_offset=image_offset)
+            eng.check_overflow()
             return sr[0] if (self.sr3 and sr.shape[0] == 1) else sr  # SR3: ret_img[-1] drops the batch axis
-        sr, tr = eng.sample(x_in, noise=noise, seed=seed, trace=True)
+        sr, tr = eng.sample(x_in, noise=noise, seed=seed, trace=True, image_offset=image_offset)
+        eng.check_overflow()
         return tr.reshape(-1, *tr.shape[2:])  # B=1: (1+frames,3,H,W) exactly as the reference
 
     @torch.no_grad()
-    def super_resolution(self, x_in, continous=False, noise=None, seed=None):
-        return self.p_sample_loop(x_in, continous, noise=noise, seed=seed)
+    def super_resolution(self, x_in, continous=False, noise=None, seed=None, image_offset=0):
+        """`image_offset`: global index of x_in[0] in a job sharded over batches / ranks (see Engine.sample)."""
+        return self.p_sample_loop(x_in, continous, noise=noise, seed=seed, image_offset=image_offset)
 
     @torch.no_grad()
     def sample(self, batch_size=1, continous=False):

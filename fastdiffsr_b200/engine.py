@@ -8,9 +8,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FdsrConfig, FdsrError
+from ._lib import FdsrConfig, FdsrError, FdsrOverflowError
 
-_DTYPES = {"fp16": _lib.DTYPE_FP16, "float16": _lib.DTYPE_FP16, "bf16": _lib.DTYPE_BF16, "bfloat16": _lib.DTYPE_BF16,
+_DTYPES = {"auto": _lib.DTYPE_FP16, "fp16": _lib.DTYPE_FP16, "float16": _lib.DTYPE_FP16, "bf16": _lib.DTYPE_BF16, "bfloat16": _lib.DTYPE_BF16,
            "fp32": _lib.DTYPE_FP32, "float32": _lib.DTYPE_FP32}  # fp32 = CUDA-core parity mode (slow)
 
 
@@ -69,8 +69,17 @@ class Engine:
 
     def _check(self, rc, what):
         if rc < 0:
-            raise FdsrError(f"{what}: {self.lib.fdsr_last_error(self._h).decode()} (code {rc})")
+            cls = FdsrOverflowError if rc == _lib.E_OVERFLOW else FdsrError
+            raise cls(f"{what}: {self.lib.fdsr_last_error(self._h).decode()} (code {rc})")
         return rc
+
+    def check_overflow(self):
+        """fp16 mode: synchronise the current stream and raise FdsrOverflowError if an activation left the fp16 range
+        since the last check (the value was stored saturated; the result is not the network's output)."""
+        if self.dtype not in ("fp16", "float16"):
+            return
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_check_overflow(self._h, self._stream()), "fdsr_check_overflow")
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -125,7 +134,10 @@ class Engine:
     def trace_frames(self):
         return self.lib.fdsr_trace_frames(self._h)
 
-    def sample(self, cond, noise=None, seed: int = 0, trace: bool = False):
+    def sample(self, cond, noise=None, seed: int = 0, trace: bool = False, image_offset: int = 0):
+        """T-step sampling of a batch.  `image_offset` = global index of cond[0] in the whole job: the built-in noise of
+        an image depends on (seed, global index, step) only, so shards of a job reproduce the unsharded result."""
+        self._check(self.lib.fdsr_set_image_offset(self._h, int(image_offset)), "fdsr_set_image_offset")
         cond = self._img(cond, "cond")
         B, _, H, W = cond.shape
         if noise is not None:
@@ -152,7 +164,19 @@ class Engine:
                                                  self._stream()), "fdsr_bicubic_u8")
         return o8, oc
 
-    def super_resolve_u8_host(self, lr_host: np.ndarray, H: int, W: int, noise=None, seed: int = 0, out=None):
+    def debug_noise(self, B: int, H: int, W: int, seed: int, stream_id: int, image_offset: int = 0):
+        """(B,3,H,W) N(0,1) values of the built-in generator for step stream `stream_id` (T: x_T, t: z of step t)."""
+        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_debug_noise(self._h, _ptr(out), B, H, W, int(seed), int(image_offset),
+                                                  int(stream_id), self._stream()), "fdsr_debug_noise")
+        return out
+
+    def graph_captures(self):
+        return int(self.lib.fdsr_graph_captures(self._h))
+
+    def super_resolve_u8_host(self, lr_host: np.ndarray, H: int, W: int, noise=None, seed: int = 0, out=None,
+                              image_offset: int = 0):
         """Host uint8 (B,h,w,3) -> host fp32 (B,3,H,W): H2D, bicubic, T-step sampling, D2H.
         `out`: optional caller-owned C-contiguous float32 (B,3,H,W) array to fill (avoids a fresh allocation per call)."""
         lr_host = np.ascontiguousarray(lr_host, dtype=np.uint8)
@@ -161,6 +185,7 @@ class Engine:
             out = np.empty((B, 3, H, W), dtype=np.float32)
         elif out.shape != (B, 3, H, W) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
             raise FdsrError(f"out must be a C-contiguous float32 array of shape {(B, 3, H, W)}")
+        self._check(self.lib.fdsr_set_image_offset(self._h, int(image_offset)), "fdsr_set_image_offset")
         with torch.cuda.device(self.device):
             self._check(self.lib.fdsr_super_resolve_u8(self._h, lr_host.ctypes.data_as(C.c_void_p), B, h, w, H, W,
                                                        _ptr(noise), seed, out.ctypes.data_as(C.c_void_p),

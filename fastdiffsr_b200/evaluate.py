@@ -33,7 +33,14 @@ def load_network(netG, opt, logger=None):
         raise FileNotFoundError(f"checkpoint {gen_path} not found (path.resume_state of the config)")
     if logger:
         logger.info('Loading pretrained model for G [{:s}] ...'.format(load_path))
-    netG.load_state_dict(torch.load(gen_path, map_location="cpu"), strict=(not opt['model']['finetune_norm']))
+    sd = torch.load(gen_path, map_location="cpu")
+    # The reference saves netG.state_dict() after set_new_noise_schedule (model/model.py:126-146), so a real
+    # `*_gen.pth` carries the 12 schedule buffers.  They load strictly when the schedule has been registered first
+    # (the reference's order, model/model.py:19-41, which `main` follows); a netG without them gets the denoiser only.
+    own = set(netG.state_dict().keys())
+    from .diffusion import _BUFFERS
+    sd = {k: v for k, v in sd.items() if not (k in _BUFFERS and k not in own)}
+    netG.load_state_dict(sd, strict=(not opt['model']['finetune_norm']))
     return True
 
 
@@ -56,7 +63,7 @@ def evaluate(netG, dataset, batch_size=16, scale=4, result_path=None, save_ext="
     start, stop, _ = shard_bounds(n_total, rank, world)
     loader = BatchLoader(dataset, batch_size, indices=range(start, stop))
     acc = torch.zeros(9, dtype=torch.float64, device=dev)       # bic[4], sr[4], n
-    if result_path and rank == 0:
+    if result_path:                  # every rank writes its own shard's images there
         os.makedirs(result_path, exist_ok=True)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -67,7 +74,9 @@ def evaluate(netG, dataset, batch_size=16, scale=4, result_path=None, save_ext="
             cond = u8_to_tensor(batch["SR"].to(dev, non_blocking=True)).contiguous()
         else:
             _, cond = eng.bicubic_u8(batch["LR"].to(dev, non_blocking=True), H, W, want_u8=False)
-        sr = netG.super_resolution(cond, False, seed=seed + 7919 * (start + bi * loader.bs))
+        # one seed for the whole job; the noise of an image depends on its global dataset index only, so the result
+        # does not depend on the batch size or the number of ranks
+        sr = netG.super_resolution(cond, False, seed=seed, image_offset=start + bi * loader.bs)
         if sr.dim() == 3:   # the SR3 baseline returns ret_img[-1] without the batch axis for a single image
             sr = sr[None]
         m_bic = eng.metrics_u8(cond, hr, scale)
@@ -153,6 +162,10 @@ def main(argv=None, default_config="config/sr_fastdiffsr_test_64_256.json", prog
     logger = setup_logger("base", paths.get('log') if isinstance(paths, dict) else None)
     dev = torch.device("cuda", local_rank)
     netG = define_G(opt).to(dev)
+    # the reference's order (model/model.py:19-41, sr_mfe.py:93-94): loss, 'train' schedule (registers the 12 buffers a
+    # checkpoint carries), strict checkpoint load, then the 'val' schedule
+    netG.set_loss(dev)
+    netG.set_new_noise_schedule(opt['model']['beta_schedule']['train'], dev)
     if not load_network(netG, opt, logger):
         logger.warning("no path.resume_state in the config: sampling with RANDOM-INIT weights")
     netG.set_new_noise_schedule(opt['model']['beta_schedule']['val'], dev)

@@ -73,7 +73,10 @@ def sharded_super_resolution(netG, cond_global: torch.Tensor, noise_global=None,
                               device=noise.device)
             noise = torch.cat([noise, pad], dim=1)
         noise = noise.contiguous()
-    sr_local = netG.super_resolution(local, False, noise=noise, seed=seed + rank)
+    # same seed on every rank + the global index of the shard's first image: the built-in noise of image k does not
+    # depend on the world size, so the gathered result equals the single-rank one bit for bit
+    start, _, _ = shard_bounds(cond_global.shape[0], rank, world)
+    sr_local = netG.super_resolution(local, False, noise=noise, seed=seed, image_offset=start)
     if sr_local.dim() == 3:   # SR3 baseline, one image per rank: ret_img[-1] has no batch axis
         sr_local = sr_local[None]
     return gather_batch(sr_local, cond_global.shape[0], group)

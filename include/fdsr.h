@@ -31,9 +31,13 @@ extern "C" {
 #define FDSR_E_CUDA -2      /* a CUDA runtime call failed */
 #define FDSR_E_STATE -3     /* call order violated (weights / schedule not loaded) */
 #define FDSR_E_NOTFOUND -4  /* unknown tensor / layer name */
+#define FDSR_E_OVERFLOW -5  /* fp16 mode: an activation left the fp16 range (stored saturated); use FDSR_DTYPE_BF16 */
 
-#define FDSR_DTYPE_FP16 0   /* fp16 operands + activations, fp32 accumulate (tcgen05 kind::f16) */
-#define FDSR_DTYPE_BF16 1   /* bf16 operands + activations, fp32 accumulate (tcgen05 kind::f16) */
+#define FDSR_DTYPE_FP16 0   /* fp16 operands + activations, fp32 accumulate (tcgen05 kind::f16).  Activation stores
+                               saturate at +-65504 and raise an overflow flag (fdsr_check_overflow) */
+#define FDSR_DTYPE_BF16 1   /* bf16 activations (fp32 exponent range: safe for a trained network's un-normalised residual
+                               stream), fp32 accumulate.  Operands: swish(GroupNorm(x)) -- bounded -- is rounded to fp16
+                               and multiplied with fp16 weights; raw inputs (1x1 residual / up / down convs) bf16 x bf16 */
 #define FDSR_DTYPE_FP32 2   /* parity mode: fp32 activations, weights and accumulation on the CUDA cores (same fused
                                layer plan; eps relative L2 <= 1e-4 against the reference; ~60x slower) */
 
@@ -86,7 +90,11 @@ int fdsr_set_schedule(fdsr_ctx* ctx, const double* betas, int32_t T);
  * ..., "posterior_mean_coef2", or "sqrt_alphas_cumprod_prev" which has T+1 entries) to host. */
 int fdsr_get_table(fdsr_ctx* ctx, const char* name, double* out_host, int32_t capacity);
 
-/* Sizes / (re)allocates the activation workspace for this shape.  Implicit in the calls below. */
+/* Sizes / (re)allocates the activation workspace for this shape.  Implicit in the calls below.  The allocation only
+ * ever grows, so the captured graphs of previously used shapes stay valid.
+ * Deviation from SURVEY 8(b), which sketched `size_t fdsr_workspace_bytes(ctx, B, H, W)` with a caller-provided
+ * workspace: the context owns its workspace (captured CUDA graphs hold pointers into it), so sizing is split into
+ * fdsr_reserve (allocate for a shape) + fdsr_workspace_bytes (bytes the current shape uses). */
 int fdsr_reserve(fdsr_ctx* ctx, int32_t B, int32_t H, int32_t W);
 size_t fdsr_workspace_bytes(const fdsr_ctx* ctx);
 
@@ -111,6 +119,19 @@ int fdsr_sample(fdsr_ctx* ctx, const float* cond_dev, const float* noise_dev, ui
                 float* sr_out_dev, float* trace_out_dev, int32_t B, int32_t H, int32_t W,
                 void* stream);
 int32_t fdsr_trace_frames(const fdsr_ctx* ctx); /* 1 + n_frames for the current schedule */
+
+/* fp16 mode only (always FDSR_OK otherwise): synchronises `stream`, then returns FDSR_E_OVERFLOW if any activation
+ * stored since the last check had left the fp16 range (it was stored saturated, so nothing downstream is inf / NaN,
+ * but the image is not the network's output), and clears the flag.  fdsr_super_resolve_u8 performs this check itself;
+ * callers of the asynchronous fdsr_sample call it when they synchronise. */
+int fdsr_check_overflow(fdsr_ctx* ctx, void* stream);
+
+/* Position of subsequent batches in the job: `first_image` is the global index of image 0 of the next fdsr_sample /
+ * fdsr_super_resolve_u8 batches.  The built-in generator's counter is (position in the image, GLOBAL image index,
+ * step), so image k of a job receives the same noise whether it is sampled alone, inside a batch, or by another rank:
+ * a batch sharded over N ranks (rank r passes the index of its first image) equals the single-rank result bit for bit.
+ * Sticky; default 0.  Read from device memory by the captured graph (no re-capture). */
+int fdsr_set_image_offset(fdsr_ctx* ctx, uint64_t first_image);
 
 /* Host-buffer convenience for callers without device memory management (the end-to-end path that
  * bench.py times): uint8 LR (B,h,w,3) host -> PIL-exact bicubic -> sampling -> fp32 SR (B,3,H,W)
@@ -162,6 +183,14 @@ int fdsr_debug_profile_unet(fdsr_ctx* ctx, int32_t t, int32_t reps, float* ms_ou
  * used by tools/role_profile.py): out_host[(cta*4 + role)*8 + slot], role 0 = MMA issuer, 1 = epilogue,
  * 2 = producer.  Re-runs op `op` on the current buffers; returns the number of entries.  Synchronous. */
 int fdsr_debug_role_cycles(fdsr_ctx* ctx, int32_t op, int32_t t, int64_t* out_host, int32_t cap, void* stream);
+/* Fills out_dev (B,3,H,W) with the N(0,1) values the built-in generator hands the sampler for step stream
+ * `stream_id` (T for x_T, t for the z of step t) of images first_image .. first_image+B-1 under `seed`: lets tests
+ * check the distribution (moments, Kolmogorov-Smirnov) and reproduce a built-in-noise sample through the
+ * injected-noise path bit for bit. */
+int fdsr_debug_noise(fdsr_ctx* ctx, float* out_dev, int32_t B, int32_t H, int32_t W, uint64_t seed,
+                     uint64_t first_image, int32_t stream_id, void* stream);
+/* Number of CUDA-graph captures of the sampling loop so far (cache misses of the per-shape graph cache). */
+int64_t fdsr_graph_captures(const fdsr_ctx* ctx);
 /* Kernel launches enqueued by this context so far (library kernels only). */
 int64_t fdsr_launch_count(const fdsr_ctx* ctx);
 /* Algorithmic conv FLOPs (2*MAC, padding counted) of one UNet forward at the reserved shape. */

@@ -79,12 +79,59 @@ def test_dataset_and_batch_loader(tmp_path):
     assert seen == [1, 2, 3, 4]
     assert len(D.LRHRDataset(root, "img", 16, 64, data_len=3)) == 3
     with pytest.raises(NotImplementedError):
-        D.LRHRDataset(root, "lmdb", 16, 64)
+        D.LRHRDataset(root, "hdf5", 16, 64)
     # sr_ folder is optional (the library rebuilds it from lr_), but one of the two must exist
     root2 = _make_dataset(str(tmp_path / "ds2"), n=2, with_sr=False)
     assert "SR" not in D.LRHRDataset(root2, "img", 16, 64).get_u8(0)
     with pytest.raises(AssertionError):
         D.LRHRDataset(str(tmp_path), "img", 16, 64)
+
+
+def test_lmdb_dataset_layout(tmp_path):
+    """datatype 'lmdb' (data/LRHR_dataset.py:17-27, 60-93): the key scheme written by prepare_data_mfe_dm.py —
+    `hr_{r}_{idx:05d}`, `sr_{l}_{r}_{idx:05d}`, `lr_{l}_{idx:05d}`, `length` — read through a key-value store.  The
+    `lmdb` package is not in this image, so the store is a dict here; with the package the same code reads a real
+    environment (and the real round trip is tested when it is importable)."""
+    from io import BytesIO
+    from PIL import Image
+    rng = np.random.default_rng(0)
+
+    def png(a):
+        buf = BytesIO()
+        Image.fromarray(a).save(buf, format="PNG")
+        return buf.getvalue()
+
+    imgs = [{"hr": rng.integers(0, 256, (64, 64, 3), dtype=np.uint8), "lr": rng.integers(0, 256, (16, 16, 3), dtype=np.uint8),
+             "sr": rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)} for _ in range(3)]
+    kv = {b"length": b"3"}
+    for i, im in enumerate(imgs):
+        kv['hr_64_{}'.format(str(i).zfill(5)).encode()] = png(im["hr"])
+        kv['sr_16_64_{}'.format(str(i).zfill(5)).encode()] = png(im["sr"])
+        kv['lr_16_{}'.format(str(i).zfill(5)).encode()] = png(im["lr"])
+    ds = D.LRHRDataset("unused", "lmdb", 16, 64, kv=kv)
+    assert len(ds) == 3
+    u8 = ds.get_u8(1)
+    assert np.array_equal(u8["HR"], imgs[1]["hr"]) and np.array_equal(u8["SR"], imgs[1]["sr"]) and np.array_equal(u8["LR"], imgs[1]["lr"])
+    assert ds[2]["HR"].shape == (3, 64, 64) and ds[2]["LR"].shape == (3, 16, 16)
+    batches = list(D.BatchLoader(ds, 2, pin=False))
+    assert [b["Index"] for b in batches] == [[0, 1], [2]] and batches[0]["HR"].shape == (2, 64, 64, 3)
+    del kv[b"hr_64_00001"]
+    with pytest.raises(KeyError):
+        ds.get_u8(1)
+    assert len(D.LRHRDataset("unused", "lmdb", 16, 64, data_len=2, kv=kv)) == 2
+    try:
+        import lmdb
+    except ImportError:
+        with pytest.raises(ImportError, match="lmdb"):
+            D.LRHRDataset(str(tmp_path), "lmdb", 16, 64)
+    else:
+        env = lmdb.open(str(tmp_path / "db"), map_size=1 << 26)
+        with env.begin(write=True) as txn:
+            for k, v in kv.items():
+                txn.put(k, v)
+        env.close()
+        real = D.LRHRDataset(str(tmp_path / "db"), "lmdb", 16, 64)
+        assert np.array_equal(real.get_u8(0)["HR"], imgs[0]["hr"])
 
 
 def test_entry_scripts_refuse_training():

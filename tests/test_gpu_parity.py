@@ -13,32 +13,34 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-DTYPE = os.environ.get("FDSR_DTYPE", "fp16")
-# north-star bar: per-step eps relative L2 <= 1e-2 in the 16-bit mode.  The default fp16 mode measures
-# ~1.5e-3.  The optional bf16 mode sits at the edge exactly as SURVEY F10 predicted (measured 0.81-1.02e-2
-# on random-init weights), so it is checked against 1.25e-2 and reported, not advertised as meeting the bar.
-EPS_TOL = 1e-2 if DTYPE == "fp16" else 1.25e-2
-LAYER_TOL = 5e-3 if DTYPE == "fp16" else 2.5e-2
+# north-star bar: per-step eps relative L2 <= 1e-2 in BOTH 16-bit modes, checked in the same pytest run (the module's
+# engine fixture is parametrized over the dtype; nothing depends on an environment variable).  fp16 measures ~1.5e-3;
+# bf16 (bf16 storage, fp16 post-GroupNorm operands — fdsr.h FDSR_DTYPE_BF16) ~5e-3.  Pure bf16 operands measured
+# 0.81-1.02e-2 in round 1, which is why the operand policy changed instead of the bar.
+EPS_TOL = 1e-2
+LAYER_TOLS = {"fp16": 5e-3, "bf16": 1e-2}   # every intermediate activation (bf16 storage rounds at 2^-9)
 
 
 def rel_l2(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-@pytest.fixture(scope="module")
-def ctx(oracle, schedule):
+@pytest.fixture(scope="module", params=["fp16", "bf16"])
+def ctx(request, oracle, schedule):
     from fastdiffsr_b200 import Engine
     assert torch.cuda.is_available(), "GPU tests need a CUDA device (no fallback exists)"
     cfg = dict(oracle.DEFAULT_UNET)
-    out = {}
+    out = {"dtype": request.param}
     for tag, jitter in (("default", 0.0), ("jitter", 0.2)):
         sd = oracle.make_state_dict(cfg, seed=0, gn_jitter=jitter)
-        eng = Engine(cfg, "cuda:0", os.environ.get("FDSR_DTYPE", "fp16"))
+        eng = Engine(cfg, "cuda:0", request.param)
         eng.load_state_dict(sd)
         eng.set_schedule(schedule["betas"])
         out[tag] = (sd, eng)
     out["cfg"] = cfg
-    return out
+    yield out
+    for tag in ("default", "jitter"):
+        out[tag][1].close()
 
 
 def test_tables_match_reference(ctx, golden_dir):
@@ -62,7 +64,7 @@ def test_unet_eps_vs_reference_golden(ctx, golden_dir, schedule, tag):
         assert abs(float(np.float32(schedule["sqrt_alphas_cumprod_prev"][t + 1])) - float(g["noise_levels"][i])) < 1e-12
         eps = eng.unet_forward(x6[:, :3].contiguous(), x6[:, 3:].contiguous(), t).cpu()
         r = rel_l2(eps, torch.from_numpy(g["eps"][i]))
-        print(f"[{tag}] t={t}: eps rel-L2 vs reference = {r:.3e}")
+        print(f"[{ctx['dtype']} {tag}] t={t}: eps rel-L2 vs reference = {r:.3e}")
         assert r <= EPS_TOL
 
 
@@ -83,7 +85,7 @@ def test_every_layer_vs_oracle(ctx, oracle, schedule):
             got = eng.read_tensor(name, B, taps[name].numel()).cpu()
             assert got.shape == taps[name].shape
             r = rel_l2(got, taps[name])
-            assert r <= LAYER_TOL, (name, r)
+            assert r <= LAYER_TOLS[ctx["dtype"]], (name, r)
     assert rel_l2(eps, eps_ref) <= EPS_TOL
 
 
@@ -106,7 +108,7 @@ def test_per_step_eps_teacher_forced(ctx, oracle, schedule):
         z = noises[20 - st["t"]].cuda() if st["t"] > 0 else None
         xp = eng.posterior_step(st["x_t"].cuda(), st["eps"].cuda(), z, st["t"]).cpu()
         assert torch.equal(xp, st["x_prev"]) or (xp - st["x_prev"]).abs().max() <= 1e-6 * st["x_prev"].abs().max()
-    print(f"worst teacher-forced eps rel-L2 over 20 steps: {worst:.3e}")
+    print(f"[{ctx['dtype']}] worst teacher-forced eps rel-L2 over 20 steps: {worst:.3e}")
 
 
 @pytest.mark.parametrize("tag", ["default", "jitter"])
@@ -217,6 +219,7 @@ def test_define_G_drop_in(ctx, oracle, golden_dir):
     """The reference-facing API: define_G -> .to(cuda) -> set_new_noise_schedule -> super_resolution."""
     import fastdiffsr_b200 as F
     opt = F.config.default_config()
+    opt["model"]["compute_dtype"] = ctx["dtype"]
     netG = F.define_G(opt)
     sd = oracle.make_state_dict(oracle.DEFAULT_UNET, seed=0)
     netG.load_state_dict(sd, strict=False)
@@ -245,7 +248,7 @@ def test_full_size_step_vs_oracle(ctx, oracle, schedule):
     ref = oracle.unet_forward(sd, cfg, torch.cat([cond, x], 1), nl)
     eps = eng.unet_forward(cond.cuda(), x.cuda(), t).cpu()
     r = rel_l2(eps, ref)
-    print(f"256x256 eps rel-L2 {r:.3e}")
+    print(f"[{ctx['dtype']}] 256x256 eps rel-L2 {r:.3e}")
     assert r <= EPS_TOL
     assert abs(eng.unet_flops() / 1e9 - 268.31) < 0.05      # SURVEY: 268.31 GFLOP per image-step at 256^2
 

@@ -159,3 +159,84 @@ def test_cabi_from_plain_c(tmp_path):
                     "-Wl,-rpath," + os.path.dirname(LIB_PATH)], check=True)
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+
+
+def test_reference_checkpoint_with_schedule_buffers_loads_through_load_network(oracle, tmp_path):
+    """the reference saves netG.state_dict() AFTER set_new_noise_schedule (model/model.py:126-146),
+    so a real `*_gen.pth` carries the 12 schedule buffers.  evaluate.load_network must accept it strictly both in the
+    reference's call order (schedule registered first, model/model.py:19-41) and on a net without the buffers."""
+    from fastdiffsr_b200 import evaluate
+    opt = default_config()
+    donor = F.define_G(opt)
+    donor.load_state_dict(oracle.make_state_dict(oracle.DEFAULT_UNET, seed=4), strict=False)
+    donor.set_new_noise_schedule(opt["model"]["beta_schedule"]["train"], "cpu")
+    full = donor.state_dict()
+    assert len(full) == 317 + 12 and "betas" in full
+    torch.save(full, str(tmp_path / "I1_E1_gen.pth"))
+    opt["path"] = {"resume_state": str(tmp_path / "I1_E1")}
+    opt["model"]["finetune_norm"] = False
+    # reference order: buffers exist at load time -> strict load of all 329 keys
+    net1 = F.define_G(opt)
+    net1.set_loss("cpu")
+    net1.set_new_noise_schedule(opt["model"]["beta_schedule"]["train"], "cpu")
+    assert evaluate.load_network(net1, opt)
+    # buffer-less net (schedule not yet set): the buffers of the checkpoint are dropped, the denoiser loads strictly
+    net2 = F.define_G(opt)
+    assert evaluate.load_network(net2, opt)
+    for net in (net1, net2):
+        assert torch.equal(net.denoise_fn.downs[0].weight, full["denoise_fn.downs.0.weight"])
+        assert torch.equal(net.state_dict()["denoise_fn.final_conv.block.3.bias"], full["denoise_fn.final_conv.block.3.bias"])
+    # a checkpoint that lacks a denoiser tensor still fails loudly under strict loading
+    broken = {k: v for k, v in full.items() if k != "denoise_fn.downs.0.weight"}
+    torch.save(broken, str(tmp_path / "I2_E2_gen.pth"))
+    opt["path"] = {"resume_state": str(tmp_path / "I2_E2")}
+    with pytest.raises(RuntimeError):
+        evaluate.load_network(F.define_G(opt), opt)
+
+
+REF_ROOT = "/root/reference/FastDiffSR"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ROOT), reason="reference tree only exists in the build container")
+def test_reference_DDPM_wrapper_runs_on_patched_define_G(oracle, tmp_path):
+    """INTEGRATION.md's one-line patch, exercised with the reference's OWN wrapper: `model.networks.define_G` replaced
+    by fastdiffsr_b200.define_G, then the unmodified `model.model.DDPM` (model/model.py:12-42) is constructed — set_device,
+    set_loss, set_new_noise_schedule('train'), strict load_network of a reference-style checkpoint (148-160),
+    print_network — and switched to the 'val' schedule as sr_mfe.py:93-94 does.  `thop` (imported by base_model.py but
+    never called on this path) is stubbed.  On this CPU-only container DDPM.test() must fail loudly (no fallback)."""
+    import sys
+    import types
+    saved_path, saved_mods = list(sys.path), set(sys.modules)
+    try:
+        thop = types.ModuleType("thop")
+        thop.profile = thop.clever_format = lambda *a, **k: None
+        sys.modules["thop"] = thop
+        sys.path.insert(0, REF_ROOT)
+        import model as RefModel
+        import model.networks as ref_networks
+        ref_define_G = ref_networks.define_G
+        ref_networks.define_G = F.define_G                      # <- the integration patch
+        opt = default_config()
+        opt["gpu_ids"] = None                                   # BaseModel: device = cpu
+        donor = ref_define_G(default_config())                   # a checkpoint written by the REFERENCE's own netG
+        donor.set_new_noise_schedule(opt["model"]["beta_schedule"]["train"], "cpu")
+        ckpt = {k: v.cpu() for k, v in donor.state_dict().items()}   # model/model.py:131-137
+        assert len(ckpt) == 317 + 12
+        torch.save(ckpt, str(tmp_path / "I9_E9_gen.pth"))
+        opt["path"] = {"resume_state": str(tmp_path / "I9_E9")}
+        m = RefModel.create_model(opt)                          # the reference's DDPM.__init__
+        assert type(m).__module__ == "model.model" and isinstance(m.netG, F.GaussianDiffusion)
+        assert m.netG.num_timesteps == 20 and m.schedule_phase == "train"
+        for k, v in ckpt.items():
+            assert torch.equal(m.netG.state_dict()[k], v), k
+        m.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], schedule_phase="val")
+        assert m.schedule_phase == "val"
+        s, n = m.get_network_description(m.netG)
+        assert n == 23802277                                    # SURVEY section 6: total parameters
+        m.feed_data({"HR": torch.zeros(1, 3, 64, 64), "SR": torch.zeros(1, 3, 64, 64), "Index": None})
+        with pytest.raises(F.FdsrError):
+            m.test(continous=False)
+    finally:
+        sys.path[:] = saved_path
+        for name in set(sys.modules) - saved_mods:
+            del sys.modules[name]

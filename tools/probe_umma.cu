@@ -167,14 +167,160 @@ static float h2f(uint16_t u, int fmt) {
   return __bfloat162float(h);
 }
 
-int main() {
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair probe (tcgen05.mma.cta_group::2, M = 256): cluster of two CTAs, CTA r holds its own 128 rows of A and
+// columns [N/2 r, N/2 r + N/2) of B (no-swizzle layouts 0 of the single-CTA probe); the leader issues.  Checks which
+// B half lands in which accumulator columns and measures the issue rate with one / two accumulators sharing B.
+struct PairParams {
+  const uint16_t* a_img;  // [2][a_bytes] smem images of A (one per CTA)
+  const uint16_t* b_img;  // [2][b_bytes] smem images of the B halves
+  float* d;               // [2][128][N]
+  long long* cycles;
+  int a_bytes, b_bytes, N, fmt, reps, two_acc;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_kernel(PairParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ((p.a_bytes + 1023) / 1024) * 1024;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < p.a_bytes / 16; i += 128)
+    reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(p.a_img + size_t(rank) * p.a_bytes / 2)[i];
+  for (int i = tid; i < p.b_bytes / 16; i += 128)
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(p.b_img + size_t(rank) * p.b_bytes / 2)[i];
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_init_fence();
+  }
+  if (warp == 0) tmem_alloc<256, true>(smem_u32(&tmem_base_s));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int NH = p.N / 2;
+  if (tid == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc_f16(256, p.N, p.fmt);
+    const uint32_t a0 = smem_u32(sA) & 0x3FFFFu, b0 = smem_u32(sB) & 0x3FFFFu;
+    uint64_t ad[KTOT / 16], bd[KTOT / 16], ad2[KTOT / 16];
+#pragma unroll
+    for (int ks = 0; ks < KTOT / 16; ++ks) {
+      ad[ks] = make_desc_nosw(a0 + (2 * ks) * APOS * 16 + BASEPOS * 16, APOS * 16, PITCH * 16);
+      ad2[ks] = make_desc_nosw(a0 + (2 * ks) * APOS * 16 + (BASEPOS - 1) * 16, APOS * 16, PITCH * 16);
+      bd[ks] = make_desc_nosw(b0 + (2 * ks) * NH * 16, NH * 16, 128);
+    }
+    const uint32_t tmem2 = (p.two_acc && p.N <= 128) ? tmem + 128 : tmem;
+    const long long t0 = clock64();
+    if (p.reps == 1) {
+#pragma unroll
+      for (int ks = 0; ks < KTOT / 16; ++ks) umma_f16_pair(tmem, ad[ks], bd[ks], idesc, ks != 0);
+    } else {
+      for (int r = 0; r < p.reps; ++r) {
+#pragma unroll
+        for (int ks = 0; ks < KTOT / 16; ++ks) {
+          umma_f16_pair(tmem, ad[ks], bd[ks], idesc, 1);
+          if (p.two_acc) umma_f16_pair(tmem2, ad2[ks], bd[ks], idesc, 1);
+        }
+      }
+    }
+    umma_commit_pair(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    p.cycles[0] = clock64() - t0;
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  for (int c = 0; c < p.N; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) p.d[(size_t(rank) * 128 + tid) * p.N + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc<256, true>(tmem);
+}
+
+static int run_pair_probe() {
+  int fails = 0;
+  CK(cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  for (int fmt = 0; fmt < 2; ++fmt)
+    for (int N : {64, 128, 256}) {
+      std::vector<float> A(256 * KTOT), B((size_t)N * KTOT);
+      srand(4321 + N + fmt);
+      for (auto& x : A) x = h2f(f2h((rand() % 2001 - 1000) / 1000.0f, fmt), fmt);
+      for (auto& x : B) x = h2f(f2h((rand() % 2001 - 1000) / 1000.0f, fmt), fmt);
+      const int a_bytes = 8 * APOS * 16, NH = N / 2, b_bytes = NH * 128;
+      std::vector<uint16_t> aimg(a_bytes, f2h(77.0f, fmt)), bimg(b_bytes, 0);  // two images each (bytes/2 elements x 2)
+      for (int r = 0; r < 2; ++r) {
+        for (int m = 0; m < 128; ++m) {
+          const int pos = BASEPOS + (m / 8) * PITCH + (m % 8);
+          for (int k = 0; k < KTOT; ++k)
+            aimg[size_t(r) * a_bytes / 2 + ((k / 8) * APOS + pos) * 8 + (k % 8)] = f2h(A[(r * 128 + m) * KTOT + k], fmt);
+        }
+        for (int n = 0; n < NH; ++n)
+          for (int k = 0; k < KTOT; ++k)
+            bimg[size_t(r) * b_bytes / 2 + ((k / 8) * NH + n) * 8 + (k % 8)] = f2h(B[(size_t)(r * NH + n) * KTOT + k], fmt);
+      }
+      uint16_t *da, *db;
+      float* dd;
+      long long* dc;
+      CK(cudaMalloc(&da, 2 * a_bytes));
+      CK(cudaMalloc(&db, 2 * b_bytes));
+      CK(cudaMalloc(&dd, 2 * 128 * N * 4));
+      CK(cudaMalloc(&dc, 8));
+      CK(cudaMemcpy(da, aimg.data(), 2 * a_bytes, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(db, bimg.data(), 2 * b_bytes, cudaMemcpyHostToDevice));
+      PairParams p{da, db, dd, dc, a_bytes, b_bytes, N, fmt, 1, 0};
+      const size_t smem = ((a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
+      probe_pair_kernel<<<2, 128, smem>>>(p);
+      CK(cudaDeviceSynchronize());
+      std::vector<float> D(2 * 128 * N);
+      CK(cudaMemcpy(D.data(), dd, D.size() * 4, cudaMemcpyDeviceToHost));
+      double maxerr = 0;
+      for (int m = 0; m < 256; ++m)
+        for (int n = 0; n < N; ++n) {
+          double ref = 0;
+          for (int k = 0; k < KTOT; ++k) ref += (double)A[m * KTOT + k] * B[(size_t)n * KTOT + k];
+          maxerr = fmax(maxerr, fabs(ref - D[m * N + n]));
+        }
+      long long cyc, cyc2;
+      p.reps = 256;
+      probe_pair_kernel<<<2, 128, smem>>>(p);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
+      p.two_acc = 1;
+      probe_pair_kernel<<<2, 128, smem>>>(p);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(&cyc2, dc, 8, cudaMemcpyDeviceToHost));
+      const bool ok = maxerr < 1e-3;
+      if (!ok) ++fails;
+      printf("pair (cta_group::2, M=256) fmt=%s N=%3d maxerr=%.3e %s  cycles/MMA(K=16)=%.1f two-acc=%.1f (ideal %d)\n",
+             fmt ? "bf16" : "fp16", N, maxerr, ok ? "OK" : "FAIL", cyc / (256.0 * 4), cyc2 / (256.0 * 8), N / 2);
+      cudaFree(da);
+      cudaFree(db);
+      cudaFree(dd);
+      cudaFree(dc);
+    }
+  return fails;
+}
+
+int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   printf("device %s sm_%d%d SMs %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  int fails = 0;
+  int fails = run_pair_probe();
+  if (argc > 1 && !strcmp(argv[1], "pair")) {
+    printf("pair probe %s (%d failures)\n", fails ? "FAILED" : "PASSED", fails);
+    return fails ? 1 : 0;
+  }
   for (int layout = 0; layout < 5; ++layout)
     for (int fmt = 0; fmt < 2; ++fmt)
       for (int N : {64, 128, 256}) {
