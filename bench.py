@@ -9,6 +9,12 @@ per GPU = BASELINE configs[1]); metric = SR images / s.  For N > 1 launch under 
 batch is sharded by image (weak scaling: 16 images per rank), each rank runs the whole loop on
 its shard, and NCCL is used once per step to all-gather the SR outputs and all-reduce the PSNR
 accumulators.  Prints ONE JSON line on rank 0.
+
+  --config 1   BASELINE configs[1] (default headline): x4 64->256, 16 images per GPU, weak scaling
+  --config 2   BASELINE configs[2]: x8 32->256, global batch 64 sharded over the N ranks (strong scaling)
+  --config 3   BASELINE configs[3]: x4 128->512 (infer_x4 / UC Merced shape), global batch 32 sharded (strong)
+  --sweep      BASELINE configs[4]: x4 64->256 global batch 1..256 on the N ranks (device-timed images/s per
+               batch size in one JSON line, next to the CPU B = 1 rate at N = 1)
 """
 import argparse
 import json
@@ -30,12 +36,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU")
-    ap.add_argument("--lr", type=int, default=64, help="LR resolution")
-    ap.add_argument("--hr", type=int, default=256, help="HR resolution")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3], help="BASELINE.json configs[k]")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: batch sweep 1..256")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (overrides the config)")
+    ap.add_argument("--lr", type=int, default=None, help="LR resolution (overrides the config)")
+    ap.add_argument("--hr", type=int, default=None, help="HR resolution (overrides the config)")
     ap.add_argument("--dtype", default=os.environ.get("FDSR_DTYPE", "fp16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # (lr, hr, global batch or None = 16 per rank, scaling)
+    lr, hr, gb, scaling = {1: (64, 256, None, "weak"), 2: (32, 256, 64, "strong"), 3: (128, 512, 32, "strong")}[a.config]
+    a.scaling = scaling if a.batch is None else "weak"
+    a.global_batch = gb if a.batch is None else None
+    if a.batch is None:
+        a.batch = 16 if gb is None else max(1, (gb + world - 1) // world)
+    a.lr = a.lr or lr
+    a.hr = a.hr or hr
+    return a
 
 
 def synthetic_lr(batch, res, seed):
@@ -135,26 +153,21 @@ def run_reference(args, rank):
     sample = f"T=20 sampling of 1 image {args.lr}->{args.hr} per step, fp32, torch CPU {cores} threads"
     out = {"impl": "reference", "metric": "sr_images_per_s_T20", "value": val, "unit": "images/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"FastDiffSR x{args.hr // args.lr} {args.lr}->{args.hr} T=20 sampling, "
-                                  f"batch {args.batch}/GPU (reference arm: bounded sample of 1 image per step)"},
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": _workload(args, 20, args.gpus) + " — reference arm: bounded sample of 1 image per step"},
            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
 
-def run_ours(args, rank, world, local_rank):
-    import numpy as np
+def _setup(args, local_rank):
     import torch
-    import torch.distributed as dist
     import fastdiffsr_b200 as F
-    from fastdiffsr_b200 import parallel as P
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a B200: there is no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    B, h, H = args.batch, args.lr, args.hr
+    h, H = args.lr, args.hr
     name = "sr_fastdiffsr_test_32_256" if h == 32 else ("sr_fastdiffsr_infer_x4" if H == 512 else "sr_fastdiffsr_test_64_256")
     opt = F.config.default_config(name)
     opt["model"]["compute_dtype"] = args.dtype
@@ -162,7 +175,26 @@ def run_ours(args, rank, world, local_rank):
     netG = F.define_G(opt).to(dev)
     netG.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], dev)
     netG.eval()
-    eng = netG.engine()
+    return dev, netG, netG.engine()
+
+
+def _workload(args, T, world):
+    h, H, B = args.lr, args.hr, args.batch
+    tag = {1: "BASELINE configs[1]", 2: "BASELINE configs[2]", 3: "BASELINE configs[3]"}[args.config]
+    if args.global_batch is None and (h, H, B) != (64, 256, 16):
+        tag = "custom shape"
+    gb = f"global batch {args.global_batch} sharded over {world} rank(s) = {B}/GPU" if args.global_batch else f"batch {B}/GPU"
+    return f"FastDiffSR x{H // h} {h}->{H} T={T} sampling, {gb} ({tag})"
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fastdiffsr_b200 import parallel as P
+
+    dev, netG, eng = _setup(args, local_rank)
+    B, h, H = args.batch, args.lr, args.hr
     T = netG.num_timesteps
 
     lr_host = synthetic_lr(B, h, 1 + rank).numpy()
@@ -171,9 +203,10 @@ def run_ours(args, rank, world, local_rank):
     g = torch.Generator().manual_seed(100 + rank)
     hr = (cond.cpu() + 0.1 * torch.nn.functional.avg_pool2d(torch.randn(B, 3, H, H, generator=g), 3, 1, 1)).clamp(-1, 1).to(dev)
     acc = torch.zeros(3, dtype=torch.float64, device=dev)
+    first_image = rank * B          # this rank's shard of the global batch (the noise of an image depends on its global index)
 
     def step_device(i):
-        sr = netG.super_resolution(cond, False, seed=1000 + i)
+        sr = netG.super_resolution(cond, False, seed=1000 + i, image_offset=first_image)
         sse = eng.sse_u8(sr, hr)
         psnr = P.psnr_from_sse(sse, 3 * H * H)
         local = torch.stack([sse.sum(), psnr.sum(), torch.tensor(float(B), dtype=torch.float64, device=dev)])
@@ -187,7 +220,7 @@ def run_ours(args, rank, world, local_rank):
     sr_host = np.zeros((B, 3, H, H), dtype=np.float32)   # caller-owned result buffer, reused every step
 
     def step_host(i):
-        return eng.super_resolve_u8_host(lr_host, H, H, seed=2000 + i, out=sr_host)
+        return eng.super_resolve_u8_host(lr_host, H, H, seed=2000 + i, out=sr_host, image_offset=first_image)
 
     def sync():
         torch.cuda.synchronize(dev)
@@ -211,7 +244,6 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps, eng.launch_count() - l0
 
-    ws_gib = None
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
@@ -222,59 +254,60 @@ def run_ours(args, rank, world, local_rank):
     value = B * world / (ms_dev / 1e3)
     e2e = B * world / (ms_e2e / 1e3)
 
+    # ---- outside the timed region: the gathered result must not depend on how the batch was sharded.  Rank 0 recomputes
+    # the FIRST image of the LAST rank alone (its LR is regenerated from that rank's seed) and compares bit for bit.
+    shard_invariant = None
+    if world > 1:
+        sr = netG.super_resolution(cond, False, seed=777, image_offset=first_image)
+        full = P.gather_batch(sr, B * world)
+        if rank == 0:
+            k = (world - 1) * B
+            lr_k = torch.from_numpy(synthetic_lr(B, h, 1 + (world - 1)).numpy()[:1]).to(dev)
+            _, cond_k = eng.bicubic_u8(lr_k, H, H, want_u8=False)
+            one = netG.super_resolution(cond_k, False, seed=777, image_offset=k)
+            shard_invariant = bool(torch.equal(one[0], full[k]))
+
     # ---- roofline of the dominant kernel (conv_gemm_kernel, tensor-bound): CUDA events around each
     # launch of a full UNet evaluation at the benchmark shape, averaged over repetitions
     # 24 back-to-back UNet evaluations (> 100 ms of continuous load); the library averages the last 12, so the
     # per-launch durations are taken at the same sustained (power-capped) clocks as the timed sampling loop
     eng.sample(cond, seed=1)
     prof = eng.profile_unet(T // 2, reps=24)
-    conv = [(n, ms, fl) for n, ms, fl in prof if fl > 0]
-    conv_ms = sum(ms for _, ms, _ in conv)
-    conv_fl = sum(fl for _, _, fl in conv)
+    exe = eng.op_flops_executed()
+    conv = [(n, ms, fl, ex) for (n, ms, fl), ex in zip(prof, exe) if fl > 0]
+    conv_ms = sum(c[1] for c in conv)
+    conv_fl = sum(c[2] for c in conv)
+    conv_ex = sum(c[3] for c in conv)
     peak, peak_src = measured_peaks()
-    achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+    ach_alg = conv_fl / (conv_ms * 1e-3) / 1e12
+    ach_exe = conv_ex / (conv_ms * 1e-3) / 1e12
     flop_per_image = eng.unet_flops() / B * T
     traffic, traffic_note = ncu_traffic()
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel": "conv_gemm_kernel (all conv layers of one UNet step)",
+    roofline = {"bound": "tensor", "achieved": ach_exe, "peak": peak, "unit": "TFLOP/s", "frac": ach_exe / peak,
+                "achieved_executed": ach_exe, "frac_executed": ach_exe / peak,
+                "achieved_algorithmic": ach_alg, "frac_algorithmic": ach_alg / peak,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "kernel": "conv_gemm_kernel (all conv layers of one UNet step)",
                 "launches_profiled": len(conv), "conv_ms_per_unet_step": conv_ms,
-                "timing": "CUDA events around each of the 52 conv launches, mean of the last 12 of 24 back-to-back UNet "
+                "timing": "CUDA events around each conv launch, mean of the last 12 of 24 back-to-back UNet "
                           "evaluations at the benchmark shape (sustained clocks)",
                 "other_ms_per_unet_step": sum(ms for _, ms, fl in prof if fl == 0),
-                "flop_accounting": "algorithmic FLOPs (2*MAC of the reference's convs, zero padding counted: 268.31 GFLOP "
-                                   "per 256^2 image per UNet step, SURVEY 8(d)); the three nearest-upsample convs are "
-                                   "executed as four 2x2 phase convs on the low-resolution input (an exact identity, "
-                                   "4/9 of their MACs: 244.15 GFLOP per image per step executed) and are accounted at their "
-                                   "algorithmic nine-tap cost; FDSR_UP_PHASES=0 runs the nine-tap form",
-                "whole_step_frac": value / world * flop_per_image / 1e12 / peak}
+                "flop_accounting": "achieved / frac = EXECUTED FLOPs (hardware utilisation): the three nearest-upsample convs "
+                                   "run as four 2x2 phase convs on the low-resolution input, 4/9 of their MACs.  "
+                                   "*_algorithmic = 2*MAC of the reference's convs, zero padding counted (268.31 GFLOP per "
+                                   "256^2 image per UNet step, SURVEY 8(d)), the figure images/s converts to",
+                "whole_step_frac_algorithmic": value / world * flop_per_image / 1e12 / peak,
+                "whole_step_frac_executed": value / world * flop_per_image / 1e12 / peak * (conv_ex / conv_fl)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import fdsr_oracle as O
-        cores = os.cpu_count()
-        torch.set_num_threads(cores)
-        sd = {k: v.detach().cpu() for k, v in netG.state_dict().items() if k.startswith("denoise_fn.")}
-        cfg = dict(O.DEFAULT_UNET)
-        tab = O.schedule_tables(O.make_beta_schedule(**O.DEFAULT_SCHEDULE))
-        c1 = cond[:1].cpu()
-        nz = torch.randn(T, 1, 3, H, H, generator=torch.Generator().manual_seed(2))
-        O.unet_forward(sd, cfg, torch.cat([c1, nz[0]], 1), torch.full((1, 1), 0.5))
-        t0 = time.perf_counter()
-        ref = O.sample_loop(sd, cfg, tab, c1, nz)
-        dt = time.perf_counter() - t0
-        ours = eng.sample(cond[:1].contiguous(), noise=nz.to(dev)).cpu()
-        cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"T=20 sampling of 1 image {h}->{H}, fp32 torch CPU, {dt:.1f} s",
-               "parity_rel_l2_vs_gpu": ((ours - ref).norm() / ref.norm()).item()}
+        cpu = cpu_baseline(netG, eng, cond, T, h, H, dev)
 
     if rank == 0:
         out = {"metric": "sr_images_per_s_T20", "value": value, "unit": "images/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-               "config": {"workload": f"FastDiffSR x{H // h} {h}->{H} T={T} sampling, batch {B}/GPU "
-                                      f"(BASELINE configs[1])" if (h, H, B) == (64, 256, 16) else
-                                      f"FastDiffSR x{H // h} {h}->{H} T={T} sampling, batch {B}/GPU",
+               "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+               "config": {"workload": _workload(args, T, world),
                           "global_batch": B * world, "parallelism": f"image-sharded x{world}",
                           "l2": "working set per step (activations %.1f GiB) exceeds the 126 MB L2; no flush needed"
                                 % ws_gib,
@@ -283,8 +316,81 @@ def run_ours(args, rank, world, local_rank):
                        "d2h_bytes_per_step": int(B * 3 * H * H * 4), "ms_per_step": ms_e2e,
                        "api": "Engine.super_resolve_u8_host -> fdsr_super_resolve_u8 (uint8 LR host -> fp32 SR host)"},
                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+               "shard_invariant": shard_invariant,
                "psnr_mean_vs_synthetic_hr": (acc[1] / acc[2]).item() if acc[2].item() > 0 else None}
         emit(out)
+
+
+def cpu_baseline(netG, eng, cond, T, h, H, dev):
+    """The oracle port of the reference's sampling loop on the box's host cores: one image, all threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fdsr_oracle as O
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().cpu() for k, v in netG.state_dict().items() if k.startswith("denoise_fn.")}
+    cfg = dict(O.DEFAULT_UNET)
+    tab = O.schedule_tables(O.make_beta_schedule(**O.DEFAULT_SCHEDULE))
+    c1 = cond[:1].cpu()
+    nz = torch.randn(T, 1, 3, H, H, generator=torch.Generator().manual_seed(2))
+    O.unet_forward(sd, cfg, torch.cat([c1, nz[0]], 1), torch.full((1, 1), 0.5))
+    t0 = time.perf_counter()
+    ref = O.sample_loop(sd, cfg, tab, c1, nz)
+    dt = time.perf_counter() - t0
+    ours = eng.sample(cond[:1].contiguous(), noise=nz.to(dev)).cpu()
+    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"T=20 sampling of 1 image {h}->{H}, fp32 torch CPU, {dt:.1f} s",
+            "parity_rel_l2_vs_gpu": ((ours - ref).norm() / ref.norm()).item()}
+
+
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE configs[4]: x4 64->256 throughput for a GLOBAL batch of 1..256 images on the N ranks (per rank
+    ceil(B/N) images; ranks beyond the batch idle by construction), device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    dev, netG, eng = _setup(args, local_rank)
+    h, H = args.lr, args.hr
+    T = netG.num_timesteps
+    rows = []
+    for gb in (1, 2, 4, 8, 16, 32, 64, 128, 256):
+        per = (gb + world - 1) // world
+        start = min(rank * per, gb)
+        mine = min(start + per, gb) - start
+        ms = torch.zeros(1, dtype=torch.float64, device=dev)
+        if mine > 0:
+            lr = torch.from_numpy(synthetic_lr(mine, h, 1 + rank).numpy()).to(dev)
+            _, cond = eng.bicubic_u8(lr, H, H, want_u8=False)
+            reps = max(2, min(8, 64 // mine))
+            for i in range(2):
+                netG.super_resolution(cond, False, seed=i, image_offset=start)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        if mine > 0:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                netG.super_resolution(cond, False, seed=10 + i, image_offset=start)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms[0] = e0.elapsed_time(e1) / reps
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rows.append({"global_batch": gb, "per_rank": per, "ms_per_batch": ms.item(), "images_per_s": gb / (ms.item() / 1e3),
+                     "ms_per_unet_step": ms.item() / T})
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        lr = torch.from_numpy(synthetic_lr(1, h, 1).numpy()).to(dev)
+        _, c1 = eng.bicubic_u8(lr, H, H, want_u8=False)
+        cpu = cpu_baseline(netG, eng, c1, T, h, H, dev)
+    if rank == 0:
+        best = max(rows, key=lambda r: r["images_per_s"])
+        emit({"metric": "sr_images_per_s_T20", "value": best["images_per_s"], "unit": "images/s", "n_gpus": world,
+              "steps": len(rows), "warmup": 2, "ms_per_step": best["ms_per_batch"], "higher_is_better": True,
+              "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+              "config": {"workload": f"FastDiffSR x{H // h} {h}->{H} T={T} sampling, global batch sweep 1..256 on "
+                                     f"{world} rank(s) (BASELINE configs[4]); value = best row"},
+              "sweep": rows, "cpu_baseline": cpu})
 
 
 def _claim_stdout():
@@ -317,7 +423,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        (run_sweep if args.sweep else run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

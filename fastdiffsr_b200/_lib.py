@@ -59,6 +59,8 @@ _SIGS = {
     "fdsr_global_error": (C.c_char_p, []),
     "fdsr_load_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_int64), C.c_int32]),
+    "fdsr_load_weights_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
     "fdsr_set_schedule": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
     "fdsr_get_table": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int32]),
     "fdsr_reserve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
@@ -85,6 +87,7 @@ _SIGS = {
     "fdsr_debug_num_ops": (C.c_int32, [C.c_void_p]),
     "fdsr_debug_op_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
     "fdsr_debug_op_flops": (C.c_double, [C.c_void_p, C.c_int32]),
+    "fdsr_debug_op_flops_executed": (C.c_double, [C.c_void_p, C.c_int32]),
     "fdsr_debug_profile_unet": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32,
                                           C.c_void_p]),
     "fdsr_debug_role_cycles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int32,

@@ -994,6 +994,7 @@ int upload_layers_f32(fdsr_ctx* c) {
       const HTensor& t = c->tensors[k.out];
       l.out = reinterpret_cast<float*>(c->d_ws + t.off);
       l.out_stats = t.stats ? reinterpret_cast<unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
+      l.out_sq_scale = stat_sq_scale((long long)l.H * l.W);
     } else {
       l.out = reinterpret_cast<float*>(c->d_ws + c->off_eps);
     }
@@ -1012,6 +1013,7 @@ int upload_layers_f32(fdsr_ctx* c) {
       g.gn_C = k.gn_C;
       g.groups = c->cfg.norm_groups;
       g.HW = (H >> t0.level) * (W >> t0.level);
+      g.sq_scale = stat_sq_scale((long long)g.HW);
       g.eps = 1e-5f;
       g.gamma = c->d_params + k.gamma_off;
       g.beta = c->d_params + k.gamma_off + k.gn_C;
@@ -1115,6 +1117,9 @@ int upload_layers(fdsr_ctx* c) {
     if (k.gn_C) {
       l.gamma = c->d_params + k.gamma_off;
       l.beta = c->d_params + k.gamma_off + k.gn_C;
+      const double hw = double(l.src[0].H) * l.src[0].W, n = double(k.gn_C / c->cfg.norm_groups) * hw;
+      l.gn_inv_sum = 1.0 / (kStatScale * n);
+      l.gn_inv_sq = 1.0 / (stat_sq_scale((long long)hw) * n);
     }
     l.bias = c->d_bias + k.bias_off;
     l.bias_tstride = k.N;
@@ -1134,6 +1139,7 @@ int upload_layers(fdsr_ctx* c) {
       } else
       l.use_tma_store = (c->tma_store && k.N >= 32 && make_out_map(&l.out_map, l.out, B, l.H, l.W, k.N, bf)) ? 1 : 0;
       l.out_stats = t.stats ? reinterpret_cast<unsigned long long*>(c->d_ws + t.stats_off) : nullptr;
+      l.out_sq_scale = float(stat_sq_scale((long long)(H >> t.level) * (W >> t.level)));
       int su = 1;
       while (su < 8 && t.unit % (4 * su) == 0) su *= 2;  // largest power of two with 2*su | unit, <= 8 pairs
       l.out_su = (l.N == 64) ? 1 : su;                    // N = 64 keeps per-pair running sums in TMEM
@@ -1169,17 +1175,17 @@ int upload_layers(fdsr_ctx* c) {
 template <int N, typename T>
 cudaError_t set_conv_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ConvCfg<N>::kSmemBytes);
+                                       ConvCfg<N, false>::kSmemBytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             ConvCfg<N>::kSmemBytes);
+                             ConvCfg<N, false>::kSmemBytes);
   if constexpr (N >= 64) {
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<N>::kSmemBytes);
+                               ConvCfg<N, true>::kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_gemm_kernel<N, T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<N>::kSmemBytes);
+                               ConvCfg<N, true>::kSmemBytes);
   }
   return e;
 }
@@ -1209,7 +1215,7 @@ int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = ConvCfg<N>::kSmemBytes;
+  cfg.dynamicSmemBytes = pair ? ConvCfg<N, true>::kSmemBytes : ConvCfg<N, false>::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1317,7 +1323,8 @@ int launch_attn(fdsr_ctx* c, int ai, cudaStream_t st) {
   const int64_t nwarp = int64_t(c->B) * HW;
   slam_pool_kernel<T><<<unsigned((nwarp * 32 + 255) / 256), 256, 0, st>>>(x, gate, sp, c->B, HW, C);
   slam_apply_kernel<T><<<dim3((HW + 7) / 8, c->B), 256, 8 * C * 4, st>>>(
-      x, gate, sp, c->d_params + a.w7_off, y, reinterpret_cast<unsigned long long*>(c->d_ws + to.stats_off), h, w, C);
+      x, gate, sp, c->d_params + a.w7_off, y, reinterpret_cast<unsigned long long*>(c->d_ws + to.stats_off), h, w, C,
+      stat_sq_scale((long long)h * w));
   CUDA_TRY(c, cudaGetLastError());
   c->launches += 4;
   return FDSR_OK;
@@ -1558,6 +1565,8 @@ int fdsr_destroy(fdsr_ctx* c) {
   return FDSR_OK;
 }
 
+static int finish_load_weights(fdsr_ctx* c);
+
 int fdsr_load_weights(fdsr_ctx* c, const char* const* names, const float* const* ptrs, const int64_t* numels,
                       int32_t n) {
   if (!c || !names || !ptrs || !numels) return fail(c, FDSR_E_INVALID, "null argument");
@@ -1566,6 +1575,27 @@ int fdsr_load_weights(fdsr_ctx* c, const char* const* names, const float* const*
     if (!names[i] || !ptrs[i] || numels[i] < 0) return fail(c, FDSR_E_INVALID, "null / negative entry %d", i);
     c->host_w[names[i]] = std::vector<float>(ptrs[i], ptrs[i] + numels[i]);
   }
+  return finish_load_weights(c);
+}
+
+int fdsr_load_weights_dev(fdsr_ctx* c, const char* const* names, const float* const* dev_ptrs, const int64_t* numels,
+                          int32_t n, void* stream) {
+  if (!c || !names || !dev_ptrs || !numels) return fail(c, FDSR_E_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  c->host_w.clear();
+  // the pointers are borrowed for the duration of the call: one device -> host copy per tensor into the repacking
+  // buffers (the repack itself — tap blobs, FiLM tables — is host code), no round trip through the caller's host memory
+  for (int i = 0; i < n; ++i) {
+    if (!names[i] || !dev_ptrs[i] || numels[i] < 0) return fail(c, FDSR_E_INVALID, "null / negative entry %d", i);
+    std::vector<float>& v = c->host_w[names[i]];
+    v.resize(size_t(numels[i]));
+    if (numels[i]) CUDA_TRY(c, cudaMemcpyAsync(v.data(), dev_ptrs[i], size_t(numels[i]) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  return finish_load_weights(c);
+}
+
+static int finish_load_weights(fdsr_ctx* c) {
   int rc = validate_weights(c);
   if (rc) {
     c->host_w.clear();
@@ -1955,14 +1985,17 @@ const char* fdsr_debug_op_name(const fdsr_ctx* c, int32_t i) {
   nm = c->attns[op.idx].name + (c->attns[op.idx].kind == 0 ? ".clam_slam" : ".attn.core");
   return nm.c_str();
 }
-double fdsr_debug_op_flops(const fdsr_ctx* c, int32_t i) {
+static double op_flops(const fdsr_ctx* c, int32_t i, bool executed) {
   if (!c || i < 0 || i >= int(c->ops.size()) || c->ops[i].kind != 0) return 0.0;
   const HConv& k = c->convs[c->ops[i].idx];
   const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
-  double macs = 0.0;
-  for (const HChunk& ch : k.chunks) macs += ch.wname == "@identity" ? 0.0 : double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
+  double macs = 0.0;  // real channels only; identity-residual chunks are bookkeeping, not convolution work
+  for (const HChunk& ch : k.chunks)
+    macs += ch.wname == "@identity" ? 0.0 : double((k.phases == 4 && !executed) ? 9 : ch.taps.size()) * ch.creal;
   return 2.0 * macs * k.cout * double(c->B) * (c->H >> lvl) * (c->W >> lvl);
 }
+double fdsr_debug_op_flops(const fdsr_ctx* c, int32_t i) { return op_flops(c, i, false); }
+double fdsr_debug_op_flops_executed(const fdsr_ctx* c, int32_t i) { return op_flops(c, i, true); }
 
 int fdsr_debug_profile_unet(fdsr_ctx* c, int32_t t, int32_t reps, float* ms_out_host, int32_t cap, void* stream) {
   if (!c || !ms_out_host) return fail(c, FDSR_E_INVALID, "null argument");

@@ -262,7 +262,7 @@ template <typename T>
 __global__ void slam_apply_kernel(const T* __restrict__ x, const float* __restrict__ gate,
                                   const float2* __restrict__ sp, const float* __restrict__ w7,
                                   T* __restrict__ out, unsigned long long* __restrict__ stats, int H, int W,
-                                  int C) {
+                                  int C, double sq_scale) {
   extern __shared__ float sacc[];  // [8 warps][C]: (sum, sumsq) per channel pair, one row per pixel/warp
   const int b = blockIdx.y;
   const int HW = H * W;
@@ -301,7 +301,7 @@ __global__ void slam_apply_kernel(const T* __restrict__ x, const float* __restri
       float t = 0.f;
       for (int w8 = 0; w8 < 8; ++w8) t += sacc[w8 * C + i];  // fixed order
       atomicAdd(&stats[int64_t(b) * C + i],   // [pair][2]: even = sum, odd = sum of squares
-                static_cast<unsigned long long>(__double2ll_rn(double(t) * ((i & 1) ? kStatScaleSq : kStatScale))));
+                static_cast<unsigned long long>(__double2ll_rn(double(t) * ((i & 1) ? sq_scale : kStatScale))));
     }
 }
 

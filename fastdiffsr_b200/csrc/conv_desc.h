@@ -104,6 +104,8 @@ struct ConvLayer {
   const void* resid;    // identity residual, NHWC 16-bit with N channels, or null
   void* out;            // NHWC 16-bit [B][H][W][N]  |  fp32 NCHW [B][out_c][H][W]
   unsigned long long* out_stats;  // [B][N/2][2] fixed point, or null
+  float out_sq_scale;   // fixed-point scale of the sums of squares of the OUTPUT tensor (power of two, see stat_sq_scale)
+  double gn_inv_sum, gn_inv_sq;  // GroupNorm input: 1 / (scale * elements per group) for the sums / sums of squares
   int32_t use_tma_store;  // 1: out_map is valid
   int32_t out_su;       // channel pairs per statistics entry (1, 2, 4, 8): coarsest unit every consumer can use
   int32_t out_mode;     // OutMode

@@ -39,6 +39,7 @@ struct F32Layer {
   const float* resid;          // identity residual NHWC fp32 [B][H][W][N] or null
   float* out;                  // NHWC fp32 [B][H][W][N] | NCHW fp32 [B][out_c][H][W]
   unsigned long long* out_stats;
+  double out_sq_scale;         // fixed-point scale of the output's sums of squares (stat_sq_scale)
   int32_t out_mode, out_c;
 };
 
@@ -47,6 +48,7 @@ struct F32GnArgs {
   const unsigned long long* stats[2];
   int32_t C[2];
   int32_t gn_C, groups, HW;
+  double sq_scale;             // fixed-point scale of the sources' sums of squares
   float eps;
   const float* gamma;
   const float* beta;
@@ -68,7 +70,7 @@ __global__ void f32_gn_table_kernel(F32GnArgs a) {
     }
     const double n = double(cpg) * a.HW;
     const double mean = double(Si) * (1.0 / 16777216.0) / n;
-    double var = double(Qi) * (1.0 / kStatScaleSq) / n - mean * mean;
+    double var = double(Qi) / a.sq_scale / n - mean * mean;
     var = var > 0.0 ? var : 0.0;
     gs[threadIdx.x] = make_float2(float(mean), float(1.0 / sqrt(var + double(a.eps))));
   }
@@ -204,9 +206,9 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const __grid_constant__ F
     if (pg == 0 && nvalid) {
       unsigned long long* st = L.out_stats + size_t(b) * L.N + n;  // pair entries: (sum, sum of squares)
       atomicAdd(st + 0, static_cast<unsigned long long>(__double2ll_rn((double(s[0]) + double(s[1])) * 16777216.0)));
-      atomicAdd(st + 1, static_cast<unsigned long long>(__double2ll_rn((double(q[0]) + double(q[1])) * kStatScaleSq)));
+      atomicAdd(st + 1, static_cast<unsigned long long>(__double2ll_rn((double(q[0]) + double(q[1])) * L.out_sq_scale)));
       atomicAdd(st + 2, static_cast<unsigned long long>(__double2ll_rn((double(s[2]) + double(s[3])) * 16777216.0)));
-      atomicAdd(st + 3, static_cast<unsigned long long>(__double2ll_rn((double(q[2]) + double(q[3])) * kStatScaleSq)));
+      atomicAdd(st + 3, static_cast<unsigned long long>(__double2ll_rn((double(q[2]) + double(q[3])) * L.out_sq_scale)));
     }
   }
 }

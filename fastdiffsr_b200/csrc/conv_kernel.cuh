@@ -45,12 +45,19 @@ constexpr int kMaxGnC = 512;
 // GroupNorm statistics are accumulated as 64-bit fixed point (2^-24 resolution): integer atomics
 // are associative, so the sums do not depend on the order in which CTAs finish.
 constexpr double kStatScale = 16777216.0;
-// sums of squares use 2^-16: per channel pair and image they reach 2 H W x^2, which at 2^-24 would wrap 63 bits once
-// the activation rms approaches 1e3 at 512^2 (possible in the bf16 mode with a trained network); 2^-16 holds
-// rms 1.6e4 at 512^2 and still resolves 1.5e-5 per tile partial sum
-constexpr double kStatScaleSq = 65536.0;
+// Sums of squares reach 2 H W x^2 per channel pair and image; at 2^-24 they would wrap 63 bits once the activation rms
+// approaches 1e3 at 512^2 (possible in the bf16 mode with a trained network).  Their scale is therefore a power of two
+// chosen per tensor from its spatial size so that an rms of 65504 — the largest value the fp16 mode can store — still
+// fits: 2^12 at 512^2, 2^14 at 256^2, ... (at most 2^24).  Producer and consumer of a tensor get it from the host.
+__host__ __device__ inline double stat_sq_scale(long long hw) {
+  int lg = 0;
+  while ((1LL << lg) < hw) ++lg;
+  int e = 30 - lg;
+  e = e < 4 ? 4 : (e > 24 ? 24 : e);
+  return double(1LL << e);
+}
 
-template <int N>
+template <int N, bool kPair = false>
 struct ConvCfg {
   static constexpr int kAccStride = N < 32 ? 32 : N;        // TMEM columns per 128-row accumulator
   static constexpr int kAccCols = 2 * kAccStride;           // two MMA tiles per CTA tile
@@ -66,13 +73,22 @@ struct ConvCfg {
 #define FDSR_B128_BYTES 32768
 #define FDSR_B128_STAGES 2
 #endif
-  static constexpr int kBStageBytes = N < 32 ? 9 * N * 128 : (N == 64 ? 24576 : (N == 128 ? FDSR_B128_BYTES : 32768));
+  // CTA pairs stage half-width blobs, so a stage of the same size holds twice the taps.  Cutting the same memory into
+  // twice as many stages of half the size (FDSR_PAIR_BSPLIT=2: more loads in flight) was measured 1.7 % SLOWER over the
+  // UNet (A/B on one box, profiles/r2/ab_bsplit.log): the MMA warp's weight waits are shared-memory bandwidth (the bulk
+  // copies' writes queue behind the tensor core's operand reads), not L2 latency, and more stages only add barrier work.
+#ifndef FDSR_PAIR_BSPLIT
+#define FDSR_PAIR_BSPLIT 1
+#endif
+  static constexpr int kBSplit = kPair ? FDSR_PAIR_BSPLIT : 1;
+  static constexpr int kBStageBytes =
+      (N < 32 ? 9 * N * 128 : (N == 64 ? 24576 : (N == 128 ? FDSR_B128_BYTES : 32768))) / kBSplit;
   // N <= 128 layers are bounded by the producer/epilogue roles, not by weight streaming: give the
   // input patch a third stage (deeper decoupling of producers and MMA) and the weights two.
   // (Measured: four patch stages with four one-tap weight stages for N = 64 removes the a_full waits
   // of the GroupNorm + 1x1-residual layers but starves the MMA warp of weights: 101 -> 132 us.)
   static constexpr int kAStages = N >= 256 ? 2 : 3;
-  static constexpr int kBStages = N >= 256 ? 3 : (N == 128 ? FDSR_B128_STAGES : 2);
+  static constexpr int kBStages = (N >= 256 ? 3 : (N == 128 ? FDSR_B128_STAGES : 2)) * kBSplit;
   // N = 64 layers that mix a GroupNorm 3x3 chunk with 1x1-residual chunks split the patch memory into
   // two rings (ConvLayer::nG / nR): two full stages for the 3x3 chunks and two 32 KB stages for the dense
   // centre boxes.  In a single ring of three the 3x3 chunk of the next tile could only be requested two
@@ -283,10 +299,18 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane)
     if (L.prof != nullptr)                                                                \
       for (int k_ = 0; k_ < 8; ++k_) L.prof[(size_t(blockIdx.x) * 4 + (role)) * 8 + k_] = pacc_[k_]; \
   } while (0)
+// timeline of one CTA (role 3): cycles since kernel entry at which an event FIRST happened (slot written once)
+#define PROF_T0 const long long pt0_ = clock64()
+#define PROF_TS(slot)                                                                      \
+  do {                                                                                     \
+    if (L.prof != nullptr) L.prof[(size_t(blockIdx.x) * 4 + 3) * 8 + (slot)] = clock64() - pt0_; \
+  } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(slot)
 #define PROF_FLUSH(role)
+#define PROF_T0
+#define PROF_TS(slot)
 #endif
 
 // kFast: GroupNorm-affine + Swish in packed fp16 (tanh form); otherwise fp32 EX2/RCP.
@@ -303,7 +327,8 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane)
 template <int N, typename T, bool kFast, bool kPair>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
-  using Cfg = ConvCfg<N>;
+  using Cfg = ConvCfg<N, kPair>;
+  PROF_T0;
   constexpr int kRow = Cfg::kRow;
   constexpr int kAStages = Cfg::kAStages;  // gathered layers: one ring of kAStages full stages
   constexpr int kASlots = Cfg::kASlots;
@@ -311,7 +336,6 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   float2* table = reinterpret_cast<float2*>(smem + Cfg::kOffTable);
-  float2* gstat = reinterpret_cast<float2*>(smem + Cfg::kOffGstat);
   float* bias_s = reinterpret_cast<float*>(smem + Cfg::kOffBias);
   float* tstat = reinterpret_cast<float*>(smem + Cfg::kOffTstat);
   const uint32_t bar0 = smem_u32(smem + Cfg::kOffBar);
@@ -372,8 +396,12 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   // Programmatic dependent launch: the next layer's CTAs may become resident (and run the prologue
   // above) as soon as SMs drain; everything that reads or writes activations / statistics waits here
   // for the previous launch to complete.  The weight loader (warp 1) only touches constant data.
+  if (tid == 0) PROF_TS(0);  // prologue done (barriers, TMEM)
   asm volatile("griddepcontrol.launch_dependents;");
-  if (warp != 1) asm volatile("griddepcontrol.wait;" ::: "memory");  // (warp 1: see the loader role)
+  // (the loader and the producer warps first fetch constants — weights, GroupNorm gamma / beta — and wait in their roles)
+  const bool is_producer = warp == 2 || warp == 3 || warp >= 4 + kEpiWarps;
+  if (warp != 1 && !is_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid == 0) PROF_TS(1);  // previous launch complete
 
   // contiguous, balanced range of tiles for this CTA: consecutive tiles share the sample (GroupNorm
   // table stays valid) and their halos (L2 locality).
@@ -484,6 +512,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           tc_fence_after();
           const bool stage_done = bq + g == taps_per_stage;
           if (leader && elect_one()) {
+            if (tile == tile_begin && c == 0 && tp0 == 0) PROF_TS(4);  // first MMA issued
             uint32_t b_lo = b_lo0 + bs * (Cfg::kBStageBytes >> 4) + bq * (blob >> 4);
             for (int tg = 0; tg < g; ++tg, b_lo += blob >> 4) {
               const uint32_t a_lo = a_stage + (cen ? 0u : (uint32_t(ck.tap_pos[tp0 + tg]) << pos_sh) + phoff);
@@ -513,7 +542,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             };
             if (stage_done) commit(bar_b_empty(bs));  // (the last, partial stage of the CTA is never waited for)
             if (tp0 + g >= ntaps) commit(bar_a_empty(as));
-            if (tp0 + g >= ntaps && c == L.nchunks - 1) commit(bar_acc_full(acc));
+            if (tp0 + g >= ntaps && c == L.nchunks - 1) {
+              commit(bar_acc_full(acc));
+              if (tile + 1 == tile_end) PROF_TS(5);  // last MMA of the CTA issued
+            }
           }
           __syncwarp();
           PROF_MARK(3);
@@ -742,6 +774,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         uint32_t raw[32];
         tmem_ld32(taddr + cb * 32, raw);
         tmem_ld_wait();
+        PROF_MARK(3);
         float v[32];
         const float4* b4 = reinterpret_cast<const float4*>(bias_s + cb * 32);
 #pragma unroll
@@ -770,14 +803,22 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             }
           }
           if constexpr (kOverflowCheck) {  // largest magnitude about to be stored as fp16 (one FMNMX3 per two values)
+            float cbmax = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) vmax = fmaxf(vmax, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+            for (int j = 0; j < 32; j += 2) cbmax = fmaxf(cbmax, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+            if (cbmax > 65504.f) {  // (rare) clamp what is stored AND what enters the statistics: everything downstream
+#pragma unroll              // stays finite; the flag tells the host that the result is not the network's output
+              for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -65504.f), 65504.f);
+            }
+            vmax = fmaxf(vmax, cbmax);
           }
+          PROF_MARK(4);
           if (use_tma && !(L.dbg & 4)) {
             // stage the warp's 32 px x 32 ch block (64B-swizzled rows), then one bulk tensor store:
             // full 64-byte segments per pixel instead of 32 scattered 16-byte writes per instruction
             if (lane == 0) bulk_wait_read0();  // previous store has drained the staging block
             __syncwarp();
+            PROF_MARK(5);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t dst = stage_s + uint32_t(lane) * 64 + uint32_t((k ^ ((lane >> 1) & 3)) * 16);
@@ -805,6 +846,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               op[k] = u;
             }
           }
+          PROF_MARK(6);
           if (do_stats && !(L.dbg & 8)) {
             // in place: v[2p] <- pair sum, v[2p+1] <- pair sum of squares (zero for masked rows)
             if (all_valid) {
@@ -879,6 +921,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               }
             }
           }
+          PROF_MARK(7);
         } else {  // fp32 NCHW, first out_c channels (final conv -> eps)
           if (valid && cb == 0) {
             float* o = reinterpret_cast<float*>(L.out);
@@ -929,7 +972,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += tstat[w8 * kRow + i];
             // entry layout [pair][2]: even = sum, odd = sum of squares
             atomicAdd(L.out_stats + size_t(b_cur) * n_full + n_off + i,
-                      static_cast<unsigned long long>(__float2ll_rn(tsum * float((i & 1) ? kStatScaleSq : kStatScale))));
+                      static_cast<unsigned long long>(__float2ll_rn(tsum * ((i & 1) ? L.out_sq_scale : float(kStatScale)))));
           }
           named_bar_sync(2, kEpiThreads);
         }
@@ -938,6 +981,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     }
     if (kOverflowCheck && vmax > 65504.f && L.flags != nullptr) atomicOr(L.flags, 1u);
     if (lane == 0) bulk_wait_all0();  // outstanding bulk tensor stores of this warp
+    if (et == 0) PROF_TS(6);  // epilogue of the last tile done, stores complete
     if (et == 0) PROF_FLUSH(1);
   } else {
     // =========================================================== input producers
@@ -951,52 +995,50 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     int ty = rem / tiles_x, tx = rem - ty * tiles_x;
     PROF_DECL;
 
-    // GroupNorm scale/shift table of sample `bb` (virtual concat of the GroupNorm sources)
-    auto build_table = [&](int bb) {
-      named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
-      const int cpg = L.gn_C / L.gn_groups;
-      // One global-load latency instead of a dependent chain: thread pv fetches the fixed-point (sum, sum of squares)
-      // of channel pair pv of the virtual concat (<= 256 pairs) into the table's own memory, used as scratch until the
-      // table is written; gamma / beta of this thread's channels are requested at the same time.
-      long long* scratch = reinterpret_cast<long long*>(table);
-      const int npairs = L.gn_C >> 1, p0 = L.src[0].C >> 1;
-      if (pidx < npairs) {
-        const int si = pidx < p0 ? 0 : 1;
-        const int pl = pidx < p0 ? pidx : pidx - p0;
-        const longlong2 st = *reinterpret_cast<const longlong2*>(
-            reinterpret_cast<const long long*>(L.src[si].stats) + (size_t(bb) * (L.src[si].C >> 1) + pl) * 2);
-        scratch[2 * pidx] = st.x;
-        scratch[2 * pidx + 1] = st.y;
-      }
-      float ga[2], be[2];
+    // GroupNorm scale/shift table of sample `bb` (virtual concat of the GroupNorm sources).
+    // Everything that does not depend on the previous launch — gamma / beta of this thread's two channels, the pair
+    // range of their groups, the reciprocals — is fetched BEFORE griddepcontrol.wait; afterwards a table costs one
+    // round of independent statistics loads (every thread sums the <= 8 channel pairs of its own group straight from
+    // L2: no staging, no cross-thread hand-off), three fp64 operations, an rsqrt and one barrier.  This sits on the
+    // critical path of every launch (statistics -> table -> first normalised patch -> first MMA).
+    const int cpg = L.gn_C > 0 ? L.gn_C / L.gn_groups : 2, ppg = cpg >> 1, p0 = L.src[0].C >> 1;
+    float ga[2] = {0.f, 0.f}, be[2] = {0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = pidx + j * kProdThreads;
-        ga[j] = c < L.gn_C ? L.gamma[c] : 0.f;
-        be[j] = c < L.gn_C ? L.beta[c] : 0.f;
+    for (int j = 0; j < 2; ++j) {
+      const int c = pidx + j * kProdThreads;
+      if (c < L.gn_C) {
+        ga[j] = L.gamma[c];
+        be[j] = L.beta[c];
       }
-      named_bar_sync(1, kProdThreads);
-      if (pidx < L.gn_groups) {
-        const int ppg = cpg >> 1;
-        long long Si = 0, Qi = 0;
-        for (int pv = pidx * ppg; pv < (pidx + 1) * ppg; ++pv) {
-          Si += scratch[2 * pv];
-          Qi += scratch[2 * pv + 1];
-        }
-        const double n = double(cpg) * L.src[0].H * L.src[0].W;
-        const double mean = double(Si) * (1.0 / kStatScale) / n;
-        double var = double(Qi) * (1.0 / kStatScaleSq) / n - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        gstat[pidx] = make_float2(float(mean), float(1.0 / sqrt(var + double(L.gn_eps))));
-      }
-      named_bar_sync(1, kProdThreads);
+    }
+    const double inv_sum = L.gn_inv_sum, inv_sq = L.gn_inv_sq;  // 1 / (fixed-point scale * elements per group), host-side
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    bool table_valid = false;
+    auto build_table = [&](int bb) {
+      if (table_valid) named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
+      table_valid = true;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int c = pidx + j * kProdThreads;
         if (c < L.gn_C) {
-          const float2 gs = gstat[c / cpg];
-          const float sc = ga[j] * gs.y;
-          const float sh = be[j] - gs.x * sc;
+          const int pv0 = (c / cpg) * ppg;
+          long long Si = 0, Qi = 0;
+#pragma unroll 8
+          for (int k = 0; k < ppg; ++k) {
+            const int pv = pv0 + k;
+            const int si = pv < p0 ? 0 : 1;
+            const int pl = pv < p0 ? pv : pv - p0;
+            const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(
+                reinterpret_cast<const long long*>(L.src[si].stats) + (size_t(bb) * (L.src[si].C >> 1) + pl) * 2));
+            Si += st.x;
+            Qi += st.y;
+          }
+          const double mean = double(Si) * inv_sum;
+          double var = double(Qi) * inv_sq - mean * mean;
+          var = var > 0.0 ? var : 0.0;
+          const float rstd = rsqrtf(float(var) + L.gn_eps);
+          const float sc = ga[j] * rstd;
+          const float sh = be[j] - float(mean) * sc;
           if constexpr (kFast && Cvt<T>::kFmt == 0) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
             table_h[c] = __float2half_rn(0.5f * sc);
             table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
@@ -1009,7 +1051,6 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       }
       named_bar_sync(1, kProdThreads);
     };
-
     if (L.a_tma != 0) {
       // ----------------------------------------------------------------- TMA-fed layers: the loader warp's
       // tensor loads land the raw 128B-swizzled patch in the stage (out-of-image positions zero);
@@ -1026,6 +1067,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         if (L.gn_C > 0 && b != cur_b) {
           cur_b = b;
           build_table(b);
+          if (pidx == 0 && tile == tile_begin) PROF_TS(2);  // GroupNorm table of the first image built
         }
         // units inside the image (padding must stay zero: swish(GN(0)) != 0)
         const int y0 = ty * kTileH - 1 + py0, x0 = tx * kTileW - 1 + px0;
@@ -1044,6 +1086,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           }
           mbar_wait(bar_raw_full(as), (rph >> as) & 1u);
           rph ^= 1u << as;
+          if (pidx == 0 && tile == tile_begin && c == 0) PROF_TS(3);  // first patch landed
           PROF_MARK(1);
           if (!(L.dbg & 2)) {
             const int cgs = (pidx & 7) ^ ((pos0 + 5 * as) & 7);
@@ -1200,6 +1243,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   tc_fence_before();
   __syncthreads();
   if (kPair) cluster_sync_all();  // neither CTA frees its TMEM / exits while the pair's MMAs or commits may still touch it
+  if (tid == 0) PROF_TS(7);
   if (warp == 0) tmem_dealloc<Cfg::kTmemCols, kPair>(tmem);
 }
 

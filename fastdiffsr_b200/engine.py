@@ -86,14 +86,22 @@ class Engine:
 
     # ---- weights / schedule
     def load_state_dict(self, sd: dict):
-        items = [(k, v.detach().to("cpu", torch.float32).contiguous()) for k, v in sd.items()
-                 if k.startswith("denoise_fn.")]
+        """Tensors that already live on this engine's GPU are handed over as device pointers (fdsr_load_weights_dev);
+        anything else goes through host memory (fdsr_load_weights)."""
+        items = [(k, v.detach()) for k, v in sd.items() if k.startswith("denoise_fn.")]
+        on_dev = bool(items) and all(v.device == self.device for _, v in items)
+        items = [(k, v.to(torch.float32).contiguous() if on_dev else v.to("cpu", torch.float32).contiguous())
+                 for k, v in items]
         n = len(items)
         names = (C.c_char_p * n)(*[k.encode() for k, _ in items])
         ptrs = (C.c_void_p * n)(*[v.data_ptr() for _, v in items])
         numels = (C.c_int64 * n)(*[v.numel() for _, v in items])
         with torch.cuda.device(self.device):
-            self._check(self.lib.fdsr_load_weights(self._h, names, ptrs, numels, n), "fdsr_load_weights")
+            if on_dev:
+                self._check(self.lib.fdsr_load_weights_dev(self._h, names, ptrs, numels, n, self._stream()),
+                            "fdsr_load_weights_dev")
+            else:
+                self._check(self.lib.fdsr_load_weights(self._h, names, ptrs, numels, n), "fdsr_load_weights")
 
     def set_schedule(self, betas):
         b = np.ascontiguousarray(np.asarray(betas, dtype=np.float64))
@@ -225,6 +233,11 @@ class Engine:
                                                         C.byref(h), C.byref(w), self._stream()), "fdsr_debug_read_tensor")
         n = B * c.value * h.value * w.value
         return buf[:n].view(B, c.value, h.value, w.value)
+
+    def op_flops_executed(self):
+        """Executed conv FLOPs per op (phase-decomposed upsample convs at 4/9 of their nine-tap cost)."""
+        n = self.lib.fdsr_debug_num_ops(self._h)
+        return [float(self.lib.fdsr_debug_op_flops_executed(self._h, i)) for i in range(n)]
 
     def profile_unet(self, t: int, reps: int = 3):
         """[(op name, mean ms, algorithmic conv FLOPs)] for one UNet evaluation at the current shape."""

@@ -81,6 +81,12 @@ const char* fdsr_global_error(void);
 int fdsr_load_weights(fdsr_ctx* ctx, const char* const* names, const float* const* host_ptrs,
                       const int64_t* numels, int32_t n);
 
+/* The same from DEVICE memory (netG.to('cuda') weights need not bounce through the caller's host
+ * memory): `dev_ptrs[i]` is a contiguous fp32 device array of numels[i] elements, borrowed for the duration of the
+ * call; copies are ordered after prior work on `stream`.  Synchronous. */
+int fdsr_load_weights_dev(fdsr_ctx* ctx, const char* const* names, const float* const* dev_ptrs,
+                          const int64_t* numels, int32_t n, void* stream);
+
 /* Replaces GaussianDiffusion.set_new_noise_schedule (diffusion.py:109-155): derives every table
  * from the T betas in float64 exactly as the reference does, and precomputes the per-step FiLM
  * bias vectors (noise level depends on t only, diffusion.py:169-170; unet.py:22-54, 242-248).
@@ -177,6 +183,9 @@ int fdsr_debug_read_tensor(fdsr_ctx* ctx, const char* name, float* out_dev, int6
 int32_t fdsr_debug_num_ops(const fdsr_ctx* ctx);
 const char* fdsr_debug_op_name(const fdsr_ctx* ctx, int32_t i);
 double fdsr_debug_op_flops(const fdsr_ctx* ctx, int32_t i);
+/* The multiply-adds the op really executes: equal to the algorithmic figure except for the three nearest-upsample convs,
+ * which run as four 2x2 phase convs on the low-resolution input (4/9 of the nine-tap MACs). */
+double fdsr_debug_op_flops_executed(const fdsr_ctx* ctx, int32_t i);
 int fdsr_debug_profile_unet(fdsr_ctx* ctx, int32_t t, int32_t reps, float* ms_out_host, int32_t cap,
                             void* stream);
 /* Role-level cycle counters of one conv op (only populated by -DFDSR_PROFILE builds of the library,

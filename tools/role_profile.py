@@ -27,7 +27,7 @@ eng.unet_forward(cond, x, 10)
 torch.cuda.synchronize()
 names = [p[0] for p in eng.profile_unet(10, reps=1)]
 MMA = ["wait acc_empty", "wait a_full", "wait b_full", "issue+commit"]
-EPI = ["wait acc_full", "drain TMEM/store/stats", "stats flush+barriers"]
+EPI = ["wait acc_full", "tile hand-off", "stats flush+barriers", "TMEM load", "bias/resid math", "staging wait", "pack+STS+TMA store", "stats"]
 PRO = ["tile setup (+GN table)", "issue loads (+table read)", "wait a_empty (+load latency)", "transform+STS+arrive"]
 for nm in want:
     op = names.index(nm)
@@ -37,6 +37,10 @@ for nm in want:
     n = int(act.sum())
     c = cyc[act].mean(axis=0)
     print(f"== {nm}: {n} CTAs; mean cycles per CTA")
+    tl = cyc[act][:, 3, :]
+    print("   timeline (cycles since kernel entry, median over CTAs): " + ", ".join(
+        f"{lab} {np.median(tl[:, i][tl[:, i] > 0]) if (tl[:, i] > 0).any() else 0:.0f}" for i, lab in enumerate(
+            ["prologue", "prev launch done", "GN table", "first patch", "first MMA", "last MMA issued", "epilogue done", "exit"])))
     for role, labels in ((0, MMA), (1, EPI), (2, PRO)):
         tot = c[role].sum()
         parts = ", ".join(f"{lab} {c[role][i]:.0f} ({100 * c[role][i] / max(tot, 1):.0f}%)" for i, lab in enumerate(labels))
