@@ -43,6 +43,16 @@ struct HChunk {
   int wc0;      // first input channel inside the weight tensor
   int creal;    // real (non-padded) channels in this chunk
   int kk = 3;   // kernel size of the weight tensor (3, or 1 for res_conv / attention projections)
+  // stem only: the packed network input is [x0 x1 x2 0 | c0 c1 c2 0 | 0 ...] (pack_input_kernel) while the reference
+  // concatenates cat([cond, x]) (diffusion.py:173): perm[j] = reference input channel of packed channel j, or -1
+  std::vector<int> perm;
+  int wchan(int ci) const { return perm.empty() ? (ci < creal ? wc0 + ci : -1) : (ci < int(perm.size()) ? perm[ci] : -1); }
+  int nreal() const {
+    if (perm.empty()) return creal;
+    int n = 0;
+    for (int v : perm) n += v >= 0;
+    return n;
+  }
 };
 struct HConv {
   std::string name;
@@ -145,6 +155,10 @@ struct fdsr_ctx {
   bool tma_in = true;    // FDSR_TMA_IN=0: producer warps gather every input patch (no TMA loads of the A operand)
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
+  bool stem_tma = true;  // FDSR_STEM_TMA=0: the 16-channel stem input is gathered by the producer warps
+  bool fused_tail = true;  // FDSR_FUSED_TAIL=0: the sampler runs pack_input / final conv -> eps / posterior as separate kernels
+  PostStep* d_post = nullptr;      // [T] per-step posterior arguments of the fused final-conv epilogue
+  ConvLayer final_fused{};         // the final conv's descriptor in kOutPosterior mode (h_layers holds the eps form)
   bool pair = true;      // FDSR_PAIR=0: never launch CTA pairs (cta_group::2); every layer runs the single-CTA kernel
   // Captured sampling loops, keyed on what the captured launches depend on: the shape and whether noise is injected /
   // a trace is written.  Seed, image offset and the noise / trace POINTERS are read from device memory (SampleArgs),
@@ -370,7 +384,9 @@ int build_plan(fdsr_ctx* c) {
     k.ncg = 2;
     k.nsrc = 1;
     k.src[0] = c->t_xin;
-    k.chunks.push_back({0, 0, 0, 0, -1, taps3x3(), "denoise_fn.downs.0.weight", 0, 6});
+    HChunk stem{0, 0, 0, 0, -1, taps3x3(), "denoise_fn.downs.0.weight", 0, 7};
+    stem.perm = {3, 4, 5, -1, 0, 1, 2};  // packed [x | 0 | cond] -> reference cat([cond, x]) channels
+    k.chunks.push_back(stem);
     k.bias_names = {"denoise_fn.downs.0.bias"};
     k.out = cur;
     c->convs.push_back(k);
@@ -510,7 +526,7 @@ int build_plan(fdsr_ctx* c) {
     if (k.gn_C > kMaxGnC) return fail(c, FDSR_E_INVALID, "layer %s: GroupNorm width %d > %d", k.name.c_str(), k.gn_C, kMaxGnC);
     const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
     double macs = 0.0;  // algorithmic: a phase layer is accounted as the nine-tap conv it replaces
-    for (const HChunk& ch : k.chunks) macs += ch.wname == "@identity" ? 0.0 : double(k.phases == 4 ? 9 : ch.taps.size()) * ch.creal;
+    for (const HChunk& ch : k.chunks) macs += ch.wname == "@identity" ? 0.0 : double(k.phases == 4 ? 9 : ch.taps.size()) * ch.nreal();
     fl += 2.0 * macs * k.cout / double(1 << (2 * lvl));
   }
   c->flops_per_px = fl;
@@ -539,7 +555,8 @@ int validate_weights(fdsr_ctx* c) {
     for (const HChunk& ch : k.chunks) {
       if (ch.wname == "@identity") continue;
       size_t& ci = cin_of[ch.wname];
-      ci = std::max(ci, size_t(ch.wc0 + ch.creal));
+      if (ch.perm.empty()) ci = std::max(ci, size_t(ch.wc0 + ch.creal));
+      else for (int v : ch.perm) ci = std::max(ci, size_t(v + 1));
       rows_of[ch.wname] = size_t(k.w_rows ? k.w_rows : k.cout);
       kk_of[ch.wname] = size_t(ch.kk);
     }
@@ -635,9 +652,9 @@ int pack_weights(fdsr_ctx* c) {
         for (int cg = 0; cg < k.ncg; ++cg)
           for (int n = 0; n < k.cout; ++n)
             for (int j = 0; j < 8; ++j) {
-              const int ci = cg * 8 + j;
-              if (ci >= ch.creal) continue;
-              const size_t wbase = (size_t(k.w_n0 + n) * cin_w + ch.wc0 + ci) * kk * kk;
+              const int wci = ch.wchan(cg * 8 + j);
+              if (wci < 0) continue;
+              const size_t wbase = (size_t(k.w_n0 + n) * cin_w + wci) * kk * kk;
               if (k.phases == 4) {
                 // tap (ry, rx) of phase (py, px): the 3x3 taps whose upsampled source row / column is that one
                 const int py = ph >> 1, px = ph & 1;
@@ -694,10 +711,13 @@ int pack_weights_f32(fdsr_ctx* c) {
       const int kk = ch.kk;
       const size_t cin_w = ch.wname == "@identity" ? 256 : w->size() / (size_t(k.w_rows ? k.w_rows : k.cout) * kk * kk);
       for (const HTap& tp : ch.taps) {
-        for (int ci = 0; ci < ch.creal; ++ci)
+        for (int ci = 0; ci < ch.creal; ++ci) {
+          const int wci = ch.wchan(ci);
+          if (wci < 0) continue;
           for (int n = 0; n < k.cout; ++n)
             host[off + size_t(ci) * k.N + n] =
-                (*w)[((size_t(k.w_n0 + n) * cin_w + ch.wc0 + ci) * kk + (is1x1 ? 0 : tp.ky)) * kk + (is1x1 ? 0 : tp.kx)];
+                (*w)[((size_t(k.w_n0 + n) * cin_w + wci) * kk + (is1x1 ? 0 : tp.ky)) * kk + (is1x1 ? 0 : tp.kx)];
+        }
         off += size_t(ch.creal) * k.N;
       }
     }
@@ -888,6 +908,16 @@ bool make_out_map_phase(CUtensorMap* m, void* ptr, int B, int h, int w, int C, i
 // strides {1, 2, 2, 1} (every second pixel in x and y: 10 x 34 positions land in shared memory)
 bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16, int kind) {
   EncodeTiledFn enc = get_encode_tiled();
+  if (kind == 3) {  // 16-channel stem input: one 8-channel plane of the patch per load (box {8, 10, 34}), no swizzle
+    if (!enc || C != 16) return false;
+    const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+    const cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+    const cuuint32_t box[4] = {8, cuuint32_t(kPatchW), cuuint32_t(kPatchH), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
+               dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   if (!enc || C < 64) return false;
   const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
   const cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
@@ -1079,7 +1109,10 @@ int upload_layers(fdsr_ctx* c) {
     }
     const bool s2d_tma = k.mode == kModeS2D && c->s2d_tma;
     l.a_tma = (c->tma_in && (k.mode == kModeNormal || s2d_tma) && k.ncg == 8) ? 1 : 0;
-    for (int s = 0; s < k.nsrc && l.a_tma; ++s)
+    if (c->tma_in && c->stem_tma && k.ncg == 2 && k.mode == kModeNormal && l.src[0].C == 16 &&
+        make_in_map(&l.in_map[0], l.src[0].ptr, B, l.src[0].H, l.src[0].W, 16, c->cfg.dtype == FDSR_DTYPE_BF16, 3))
+      l.a_tma = 2;  // the stem: two 8-channel TMA plane loads per tile, no producer work
+    for (int s = 0; s < k.nsrc && l.a_tma == 1; ++s)
       if (!make_in_map(&l.in_map[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
                        c->cfg.dtype == FDSR_DTYPE_BF16, 0) ||
           !make_in_map(&l.in_map_c[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
@@ -1165,6 +1198,13 @@ int upload_layers(fdsr_ctx* c) {
     }
   }
   static_assert(sizeof(ConvLayer) <= 4000, "ConvLayer must fit the kernel parameter space");
+  // the sampler's form of the final conv: eps stays in registers, the epilogue performs the posterior update
+  c->final_fused = L.back();
+  c->final_fused.out_mode = kOutPosterior;
+  c->final_fused.post = c->d_post;
+  c->final_fused.x_state = reinterpret_cast<float*>(c->d_ws + c->off_x);
+  c->final_fused.xin = c->d_ws + c->tensors[c->t_xin].off;
+  c->final_fused.args = reinterpret_cast<const SampleArgs*>(c->d_ws + c->off_seed);
   c->h_layers = L;
   const int rc = upload_attn(c);
   if (rc) return rc;
@@ -1199,10 +1239,11 @@ cudaError_t set_conv_attrs() {
 }
 
 template <typename T>
-int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st);
+int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st, const ConvLayer* override_layer = nullptr);
 
 template <int N, typename T>
-int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
+int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st, const ConvLayer* override_layer) {
+  const ConvLayer& LY = override_layer ? *override_layer : c->h_layers[li];
   const bool pair = c->h_layers[li].pair != 0;
   const int cs = pair ? 2 : 1;  // CTA pairs are clusters of two; the unit of work is then a pair of tiles
   const int ngroups = ntiles / cs / c->h_layers[li].group;
@@ -1229,37 +1270,37 @@ int launch_conv_t(fdsr_ctx* c, int li, int ntiles, int t, cudaStream_t st) {
   const bool fast = !c->precise;
   if constexpr (N >= 64) {
     if (pair) {
-      if (fast) CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, true, true>, c->h_layers[li], t));
-      else CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false, true>, c->h_layers[li], t));
+      if (fast) CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, true, true>, LY, t));
+      else CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false, true>, LY, t));
       CUDA_TRY(c, cudaGetLastError());
       ++c->launches;
       return FDSR_OK;
     }
   }
   if (fast)
-    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, true, false>, c->h_layers[li], t));
+    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, true, false>, LY, t));
   else
-    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false, false>, c->h_layers[li], t));
+    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N, T, false, false>, LY, t));
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
   return FDSR_OK;
 }
 
 template <typename T>
-int launch_conv(fdsr_ctx* c, int li, int t, cudaStream_t st) {
+int launch_conv(fdsr_ctx* c, int li, int t, cudaStream_t st, const ConvLayer* override_layer = nullptr) {
   if constexpr (sizeof(T) == 4) return launch_conv_f32(c, li, t, st);
-  else return launch_conv16<T>(c, li, t, st);
+  else return launch_conv16<T>(c, li, t, st, override_layer);
 }
 
 template <typename T>
-int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st) {
+int launch_conv16(fdsr_ctx* c, int li, int t, cudaStream_t st, const ConvLayer* override_layer) {
   const HConv& k = c->convs[li];
   const int ntiles = c->h_layers[li].ntiles;
   switch (c->h_layers[li].N) {
-    case 16: return launch_conv_t<16, T>(c, li, ntiles, t, st);
-    case 64: return launch_conv_t<64, T>(c, li, ntiles, t, st);
-    case 128: return launch_conv_t<128, T>(c, li, ntiles, t, st);
-    case 256: return launch_conv_t<256, T>(c, li, ntiles, t, st);
+    case 16: return launch_conv_t<16, T>(c, li, ntiles, t, st, override_layer);
+    case 64: return launch_conv_t<64, T>(c, li, ntiles, t, st, override_layer);
+    case 128: return launch_conv_t<128, T>(c, li, ntiles, t, st, override_layer);
+    case 256: return launch_conv_t<256, T>(c, li, ntiles, t, st, override_layer);
   }
   return fail(c, FDSR_E_INVALID, "unsupported N=%d", k.N);
 }
@@ -1330,30 +1371,51 @@ int launch_attn(fdsr_ctx* c, int ai, cudaStream_t st) {
   return FDSR_OK;
 }
 
-// One UNet evaluation on the context's internal cond / x buffers -> internal eps buffer.
 template <typename T>
-int unet_internal(fdsr_ctx* c, int t, cudaStream_t st) {
-  if (c->layers_dirty) {
-    int rc = upload_layers(c);
-    if (rc) return rc;
-  }
-  CUDA_TRY(c, cudaMemsetAsync(c->d_ws + c->stats_off, 0, c->stats_bytes, st));
+int pack_input(fdsr_ctx* c, cudaStream_t st) {
   const int HW = c->H * c->W;
   const int64_t npix = int64_t(c->B) * HW;
   pack_input_kernel<T><<<unsigned((npix + 255) / 256), 256, 0, st>>>(
       reinterpret_cast<const float*>(c->d_ws + c->off_cond), reinterpret_cast<const float*>(c->d_ws + c->off_x),
       reinterpret_cast<T*>(c->d_ws + c->tensors[c->t_xin].off), c->B, HW);
+  CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
-  for (const HOp& op : c->ops) {
-    int rc = op.kind == 0 ? launch_conv<T>(c, op.idx, t, st) : launch_attn<T>(c, op.idx, st);
+  return FDSR_OK;
+}
+
+// One UNet evaluation on the context's internal cond / x buffers.
+//   fused = false: cat[cond, x] is packed first and eps lands in the internal eps buffer (the fdsr_unet_forward hook);
+//   fused = true (sampler): the packed input already holds x_t (written by the previous step's epilogue) and the final
+//                  conv's epilogue turns eps into x_{t-1} in place (kOutPosterior) — no pack / posterior launches.
+template <typename T>
+int unet_internal(fdsr_ctx* c, int t, cudaStream_t st, bool fused) {
+  if (c->layers_dirty) {
+    int rc = upload_layers(c);
+    if (rc) return rc;
+  }
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ws + c->stats_off, 0, c->stats_bytes, st));
+  if (!fused) {
+    int rc = pack_input<T>(c, st);
+    if (rc) return rc;
+  }
+  for (size_t i = 0; i < c->ops.size(); ++i) {
+    const HOp& op = c->ops[i];
+    const bool last = fused && i + 1 == c->ops.size();
+    int rc = op.kind == 0 ? launch_conv<T>(c, op.idx, t, st, last ? &c->final_fused : nullptr) : launch_attn<T>(c, op.idx, st);
     if (rc) return rc;
   }
   return FDSR_OK;
 }
 
-int unet_dispatch(fdsr_ctx* c, int t, cudaStream_t st) {
-  if (c->cfg.dtype == FDSR_DTYPE_FP32) return unet_internal<float>(c, t, st);
-  return c->cfg.dtype == FDSR_DTYPE_BF16 ? unet_internal<__nv_bfloat16>(c, t, st) : unet_internal<__half>(c, t, st);
+// the fused tail exists for the 16-bit tensor-core path of the FastDiffSR model
+bool can_fuse_tail(const fdsr_ctx* c) {
+  return c->fused_tail && c->cfg.dtype != FDSR_DTYPE_FP32 && c->cfg.model == FDSR_MODEL_FASTDIFFSR && c->d_post != nullptr;
+}
+
+int unet_dispatch(fdsr_ctx* c, int t, cudaStream_t st, bool fused = false) {
+  if (c->cfg.dtype == FDSR_DTYPE_FP32) return unet_internal<float>(c, t, st, false);
+  return c->cfg.dtype == FDSR_DTYPE_BF16 ? unet_internal<__nv_bfloat16>(c, t, st, fused)
+                                         : unet_internal<__half>(c, t, st, fused);
 }
 
 int check_ready(fdsr_ctx* c) {
@@ -1366,10 +1428,10 @@ int check_ready(fdsr_ctx* c) {
 // injected noise / the generator's stream t
 int posterior_launch(fdsr_ctx* c, const float* x, const float* eps, const float* z, int t, float* out,
                      int64_t numel_img, int images, const SampleArgs* args, int64_t z_block, cudaStream_t st) {
-  if (numel_img % 4 || numel_img / 4 > 0x7fffffffLL || images < 1 || images > 65535)
-    return fail(c, FDSR_E_INVALID, "posterior: per-image element count must be a multiple of 4 (< 2^33), 1..65535 images");
-  const uint32_t n4 = uint32_t(numel_img / 4);
-  posterior_kernel<<<dim3((n4 + 255) / 256, images), 256, 0, st>>>(x, eps, z, out, n4, c->post[t], args, z_block,
+  if (numel_img % 3 || numel_img / 3 > 0x7fffffffLL || images < 1 || images > 65535)
+    return fail(c, FDSR_E_INVALID, "posterior: images are (3,H,W) blocks, 1..65535 of them");
+  const uint32_t hw = uint32_t(numel_img / 3);
+  posterior_kernel<<<dim3((hw + 255) / 256, images), 256, 0, st>>>(x, eps, z, out, hw, c->post[t], args, z_block,
                                                                     uint32_t(t), t > 0 ? 1 : 0);
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
@@ -1388,8 +1450,7 @@ int sample_enqueue(fdsr_ctx* c, bool has_noise, bool has_trace, cudaStream_t st)
   float* sr = reinterpret_cast<float*>(c->d_ws + c->off_sr);
   const int nfr = fdsr_trace_frames(c);
   const unsigned gb = unsigned((numel + 255) / 256);
-  const uint32_t n4 = uint32_t(per / 4);
-  noise_init_kernel<<<dim3((n4 + 255) / 256, B), 256, 0, st>>>(x, n4, args, uint32_t(T));
+  noise_init_kernel<<<dim3((uint32_t(c->H) * c->W + 255) / 256, B), 256, 0, st>>>(x, uint32_t(c->H) * c->W, args, uint32_t(T));
   ++c->launches;
   // FastDiffSR predicts the residual: frames and result go through res2img (diffusion.py:213-216, 275-281).
   // The SR3 baseline predicts the image: frames are the raw x, the first frame is the conditioning image itself
@@ -1402,11 +1463,22 @@ int sample_enqueue(fdsr_ctx* c, bool has_noise, bool has_trace, cudaStream_t st)
     frame = 1;
   }
   const int inter = 1 | (T / 10);
+  const bool fused = can_fuse_tail(c);
+  if (fused) {  // cat[cond, x_T] once; afterwards every step's epilogue rewrites the x channels of the packed input
+    if (c->layers_dirty) {
+      int rc = upload_layers(c);
+      if (rc) return rc;
+    }
+    int rc = c->cfg.dtype == FDSR_DTYPE_BF16 ? pack_input<__nv_bfloat16>(c, st) : pack_input<__half>(c, st);
+    if (rc) return rc;
+  }
   for (int k = 0, t = T - 1; t >= 0; --t, ++k) {
-    int rc = unet_dispatch(c, t, st);
+    int rc = unet_dispatch(c, t, st, fused);
     if (rc) return rc;
-    rc = posterior_launch(c, x, eps, nullptr, t, x, per, B, args, k + 1, st);
-    if (rc) return rc;
+    if (!fused) {
+      rc = posterior_launch(c, x, eps, nullptr, t, x, per, B, args, k + 1, st);
+      if (rc) return rc;
+    }
     if (has_trace && t % inter == 0) {
       res2img_kernel<<<gb, 256, 0, st>>>(x, cond, nullptr, per, per * nfr, B, args, per * frame, sr3);
       ++c->launches;
@@ -1503,6 +1575,10 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tma_store = !(e2 && e2[0] == '0');
     const char* e3 = getenv("FDSR_PAIR");
     c->pair = !(e3 && e3[0] == '0');
+    const char* e13 = getenv("FDSR_STEM_TMA");
+    c->stem_tma = !(e13 && e13[0] == '0');
+    const char* e14 = getenv("FDSR_FUSED_TAIL");
+    c->fused_tail = !(e14 && e14[0] == '0');
     const char* e4 = getenv("FDSR_SPLIT_N");
     c->split_n = !(e4 && e4[0] == '0');
     const char* e5 = getenv("FDSR_PDL");
@@ -1550,6 +1626,7 @@ int fdsr_destroy(fdsr_ctx* c) {
   cudaFree(c->d_weights32);
   cudaFree(c->d_params);
   cudaFree(c->d_bias);
+  cudaFree(c->d_post);
   cudaFree(c->d_ws);
   cudaFree(c->d_prof);
   cudaFree(c->d_bic_tmp);
@@ -1658,6 +1735,15 @@ int fdsr_set_schedule(fdsr_ctx* c, const double* betas, int32_t T) {
   c->post.resize(T);
   for (int i = 0; i < T; ++i)
     c->post[i] = PostCoef{float(s_r[i]), float(s_rm1[i]), float(c1[i]), float(c2[i]), expf(0.5f * float(plv[i]))};
+  {  // per-step arguments of the fused final-conv epilogue: step t is the (T-1-t)-th of the loop, its z block T-t
+    std::vector<PostStep> ps(T);
+    for (int t = 0; t < T; ++t) ps[t] = PostStep{c->post[t], T - t, t > 0 ? 1 : 0, {0}};
+    cudaFree(c->d_post);
+    c->d_post = nullptr;
+    CUDA_TRY(c, cudaMalloc(&c->d_post, sizeof(PostStep) * size_t(T)));
+    CUDA_TRY(c, cudaMemcpy(c->d_post, ps.data(), sizeof(PostStep) * size_t(T), cudaMemcpyHostToDevice));
+    c->layers_dirty = true;
+  }
   c->drop_graphs();
   return build_bias_tables(c);
 }
@@ -1763,10 +1849,10 @@ int fdsr_posterior_step(fdsr_ctx* c, const float* xt, const float* eps, const fl
   if (c->T == 0) return fail(c, FDSR_E_STATE, "fdsr_set_schedule has not been called");
   if (t < 0 || t >= c->T) return fail(c, FDSR_E_INVALID, "t out of range");
   if (t > 0 && !z) return fail(c, FDSR_E_INVALID, "z is required for t > 0");
-  if (numel < 4 || numel % 4) return fail(c, FDSR_E_INVALID, "numel must be a positive multiple of 4");
-  // one "image" of numel floats when it fits the per-image limit, else split into equal blocks
+  if (numel < 3 || numel % 3) return fail(c, FDSR_E_INVALID, "numel must be a positive multiple of 3 ((B,3,H,W) tensors)");
+  // elementwise with an explicit z: treated as one (3, numel/3) image (split into equal blocks if it is huge)
   int64_t blocks = 1;
-  while (numel % blocks != 0 || (numel / blocks) / 4 > 0x7fffffffLL) ++blocks;
+  while (numel % (3 * blocks) != 0 || (numel / blocks) / 3 > 0x7fffffffLL) ++blocks;
   return posterior_launch(c, xt, eps, z, t, out, numel / blocks, int(blocks), nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -1991,7 +2077,7 @@ static double op_flops(const fdsr_ctx* c, int32_t i, bool executed) {
   const int lvl = k.out >= 0 ? c->tensors[k.out].level : 0;
   double macs = 0.0;  // real channels only; identity-residual chunks are bookkeeping, not convolution work
   for (const HChunk& ch : k.chunks)
-    macs += ch.wname == "@identity" ? 0.0 : double((k.phases == 4 && !executed) ? 9 : ch.taps.size()) * ch.creal;
+    macs += ch.wname == "@identity" ? 0.0 : double((k.phases == 4 && !executed) ? 9 : ch.taps.size()) * ch.nreal();
   return 2.0 * macs * k.cout * double(c->B) * (c->H >> lvl) * (c->W >> lvl);
 }
 double fdsr_debug_op_flops(const fdsr_ctx* c, int32_t i) { return op_flops(c, i, false); }
@@ -2090,14 +2176,13 @@ int fdsr_set_image_offset(fdsr_ctx* c, uint64_t first_image) {
 
 int fdsr_debug_noise(fdsr_ctx* c, float* out, int32_t B, int32_t H, int32_t W, uint64_t seed, uint64_t first_image,
                      int32_t stream_id, void* stream) {
-  if (!c || !out || B < 1 || B > 65535 || H < 1 || W < 1 || (int64_t(3) * H * W) % 4)
-    return fail(c, FDSR_E_INVALID, "bad argument (3*H*W must be a multiple of 4)");
+  if (!c || !out || B < 1 || B > 65535 || H < 1 || W < 1) return fail(c, FDSR_E_INVALID, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SampleArgs* slot = nullptr;  // a private argument slot: the workspace may not exist yet
   CUDA_TRY(c, cudaMallocAsync(reinterpret_cast<void**>(&slot), sizeof(SampleArgs), st));
   set_args_kernel<<<1, 1, 0, st>>>(slot, SampleArgs{seed, first_image, nullptr, nullptr});
-  const uint32_t n4 = uint32_t(int64_t(3) * H * W / 4);
-  noise_init_kernel<<<dim3((n4 + 255) / 256, B), 256, 0, st>>>(out, n4, slot, uint32_t(stream_id));
+  const uint32_t hw = uint32_t(H) * uint32_t(W);
+  noise_init_kernel<<<dim3((hw + 255) / 256, B), 256, 0, st>>>(out, hw, slot, uint32_t(stream_id));
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaFreeAsync(slot, st));
   c->launches += 2;

@@ -10,56 +10,35 @@
 namespace fdsr {
 
 // ------------------------------------------------------------------------------------------
-// Counter-based Gaussian noise: Philox4x32-10 keyed by the seed.  The counter is (position inside the image / 4,
-// GLOBAL image index, stream): the noise of an image depends on the seed, the image's index in the whole job and
-// the step only — not on the batch it happens to be sampled in, nor on which rank samples it — so a batch sharded
-// over N ranks reproduces the single-rank result bit for bit.  Streams: T for x_T, t for the z of step t.
+// Counter-based Gaussian noise: Philox4x32-10 keyed by the seed.  The counter is (PIXEL index inside the image,
+// GLOBAL image index, stream) and one block of four normals serves the three channels of that pixel (the fourth is
+// unused), so the thread that owns a pixel — in particular the final conv's epilogue thread, which performs the
+// posterior update in registers — needs exactly one Philox evaluation.  The noise of an image depends on the seed, the
+// image's index in the whole job and the step only — not on the batch it happens to be sampled in, nor on which rank
+// samples it — so a batch sharded over N ranks reproduces the single-rank result bit for bit.
+// Streams: T for x_T, t for the z of step t.
 // Used when the caller does not inject noise (the reference draws torch.randn on the device,
 // diffusion.py:189,207; any N(0,1) stream is an equally valid sample of the same sampler).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream, uint64_t image, uint32_t idx4) {
-  const uint4 r = philox4x32_10(make_uint4(idx4, uint32_t(image), stream, 0x5eedu + uint32_t(image >> 32)),
-                                make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
-  const float k = 2.3283064365386963e-10f;  // 2^-32
-  const float u0 = (float(r.x) + 0.5f) * k, u1 = (float(r.y) + 0.5f) * k;
-  const float u2 = (float(r.z) + 0.5f) * k, u3 = (float(r.w) + 0.5f) * k;
-  const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
-  float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * u1, &s0, &c0);
-  __sincosf(6.283185307179586f * u3, &s1, &c1);
-  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
-}
-
-// Per-call arguments of the sampler that live in DEVICE memory, so that one captured CUDA graph per
-// (B, H, W, injected-noise?, trace?) serves every seed, image offset, noise tensor and trace tensor.
-struct SampleArgs {
-  uint64_t seed;         // Philox key
-  uint64_t image0;       // global index of the first image of this batch
-  const float* noise;    // (T,B,3,H,W) injected noise, or null: built-in generator
-  float* trace;          // (B, frames, 3, H, W), or null
-};
 __global__ void set_args_kernel(SampleArgs* slot, SampleArgs a) { *slot = a; }
 
-// x_T: the first (B,3,H,W) block of the injected noise, or stream T of the generator.  grid (n4_img / 256, B)
-__global__ void noise_init_kernel(float* __restrict__ out, uint32_t n4_img, const SampleArgs* __restrict__ args,
+// x_T: the first (B,3,H,W) block of the injected noise, or stream T of the generator.  grid (HW / 256, B), thread = pixel
+__global__ void noise_init_kernel(float* __restrict__ out, uint32_t HW, const SampleArgs* __restrict__ args,
                                   uint32_t stream) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4_img) return;
-  const size_t o = size_t(blockIdx.y) * n4_img + i;
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const size_t o = size_t(blockIdx.y) * 3 * HW + p;
   const float* nz = args->noise;
-  reinterpret_cast<float4*>(out)[o] = nz != nullptr ? reinterpret_cast<const float4*>(nz)[o]
-                                                    : philox_normal4(args->seed, stream, args->image0 + blockIdx.y, i);
+  if (nz != nullptr) {
+    out[o] = nz[o];
+    out[o + HW] = nz[o + HW];
+    out[o + 2 * size_t(HW)] = nz[o + 2 * size_t(HW)];
+  } else {
+    const float4 z = philox_normal4(args->seed, stream, args->image0 + blockIdx.y, p);
+    out[o] = z.x;
+    out[o + HW] = z.y;
+    out[o + 2 * size_t(HW)] = z.z;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -78,6 +57,9 @@ __device__ __forceinline__ void st_pair(T* p, float a, float b) {
   else *reinterpret_cast<uint32_t*>(p) = Cvt<T>::pack(a, b);
 }
 
+// Channel order of the packed input: [x0 x1 x2 0 | c0 c1 c2 0 | 0 ...] (x_t first, so that the fused posterior
+// epilogue of the final conv rewrites it with one aligned 8-byte store per pixel); the stem weights are packed with
+// the matching permutation of the reference's cat([cond, x]) order (kXinPerm in api.cu).
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ cond, const float* __restrict__ x,
                                   T* __restrict__ out, int B, int HW) {
@@ -89,16 +71,16 @@ __global__ void pack_input_kernel(const float* __restrict__ cond, const float* _
   const float* xp = x + int64_t(b) * 3 * HW + p;
   if constexpr (sizeof(T) == 4) {
     float4* o = reinterpret_cast<float4*>(out + i * 16);
-    o[0] = make_float4(cp[0], cp[HW], cp[2 * HW], xp[0]);
-    o[1] = make_float4(xp[HW], xp[2 * HW], 0.f, 0.f);
+    o[0] = make_float4(xp[0], xp[HW], xp[2 * HW], 0.f);
+    o[1] = make_float4(cp[0], cp[HW], cp[2 * HW], 0.f);
     o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
     o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     uint4 lo, hi = make_uint4(0u, 0u, 0u, 0u);
-    lo.x = Cvt<T>::pack(cp[0], cp[HW]);
-    lo.y = Cvt<T>::pack(cp[2 * HW], xp[0]);
-    lo.z = Cvt<T>::pack(xp[HW], xp[2 * HW]);
-    lo.w = 0u;
+    lo.x = Cvt<T>::pack(xp[0], xp[HW]);
+    lo.y = Cvt<T>::pack(xp[2 * HW], 0.f);
+    lo.z = Cvt<T>::pack(cp[0], cp[HW]);
+    lo.w = Cvt<T>::pack(cp[2 * HW], 0.f);
     uint4* o = reinterpret_cast<uint4*>(out + i * 16);
     o[0] = lo;
     o[1] = hi;
@@ -111,41 +93,31 @@ __global__ void pack_input_kernel(const float* __restrict__ cond, const float* _
 //   x0 = clamp(a*x - b*eps, -1, 1);  mean = c1*x0 + c2*x;  x_prev = mean + z*sigma
 // z comes from `z` (injected) or from the Philox stream when z == nullptr and seed != nullptr.
 // ------------------------------------------------------------------------------------------
-struct PostCoef {
-  float a, b, c1, c2, sigma;
-};
-__device__ __forceinline__ float post1(float x, float e, float z, const PostCoef& k) {
-  float x0 = __fsub_rn(__fmul_rn(k.a, x), __fmul_rn(k.b, e));
-  x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-  const float mean = __fadd_rn(__fmul_rn(k.c1, x0), __fmul_rn(k.c2, x));
-  return __fadd_rn(mean, __fmul_rn(z, k.sigma));
-}
-// grid (n4_img / 256, B).  z: explicit tensor (fdsr_posterior_step), else block `z_block` of args->noise, else the
-// generator's stream `stream`; add_noise = 0 (t == 0): z = 0.
+// grid (HW / 256, B), thread = pixel (3 channels).  z: explicit tensor (fdsr_posterior_step), else block `z_block` of
+// args->noise, else the generator's stream `stream`; add_noise = 0 (t == 0): z = 0.
 __global__ void posterior_kernel(const float* __restrict__ x, const float* __restrict__ eps,
-                                 const float* __restrict__ z, float* __restrict__ out, uint32_t n4_img,
+                                 const float* __restrict__ z, float* __restrict__ out, uint32_t HW,
                                  PostCoef k, const SampleArgs* __restrict__ args, int64_t z_block, uint32_t stream,
                                  int add_noise) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4_img) return;
-  const size_t o = size_t(blockIdx.y) * n4_img + i;
-  const float4 xv = reinterpret_cast<const float4*>(x)[o];
-  const float4 ev = reinterpret_cast<const float4*>(eps)[o];
-  float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const size_t o = size_t(blockIdx.y) * 3 * HW + p;
+  float zv[3] = {0.f, 0.f, 0.f};
   if (add_noise) {
-    if (z != nullptr) zv = reinterpret_cast<const float4*>(z)[o];
-    else if (args != nullptr) {
-      const float* nz = args->noise;
-      if (nz != nullptr) zv = reinterpret_cast<const float4*>(nz)[size_t(z_block) * gridDim.y * n4_img + o];
-      else zv = philox_normal4(args->seed, stream, args->image0 + blockIdx.y, i);
+    const float* nz = z != nullptr ? z : (args != nullptr && args->noise != nullptr
+                                              ? args->noise + size_t(z_block) * gridDim.y * 3 * HW : nullptr);
+    if (nz != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) zv[c] = nz[o + size_t(c) * HW];
+    } else if (args != nullptr) {
+      const float4 r = philox_normal4(args->seed, stream, args->image0 + blockIdx.y, p);
+      zv[0] = r.x;
+      zv[1] = r.y;
+      zv[2] = r.z;
     }
   }
-  float4 r;
-  r.x = post1(xv.x, ev.x, zv.x, k);
-  r.y = post1(xv.y, ev.y, zv.y, k);
-  r.z = post1(xv.z, ev.z, zv.z, k);
-  r.w = post1(xv.w, ev.w, zv.w, k);
-  reinterpret_cast<float4*>(out)[o] = r;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[o + size_t(c) * HW] = post1(x[o + size_t(c) * HW], eps[o + size_t(c) * HW], zv[c], k);
 }
 
 // res2img (diffusion.py:275-281): clamp(x,-1,1)/2 + cond.  `out` rows may be strided per sample

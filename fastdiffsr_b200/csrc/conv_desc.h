@@ -23,6 +23,8 @@ constexpr int kPatchH = kTileH + 2;
 constexpr int kPatchPos = kPatchW * kPatchH;  // 340 positions
 constexpr int kPlanePos = 341;                // odd => conflict-free 16B stores across channel groups
 constexpr int kPlaneBytes = kPlanePos * 16;
+constexpr int kPlaneBytesTma = 344 * 16;      // plane pitch when the planes are written by TMA (a_tma = 2): bulk tensor
+                                              // copies need a 128-byte aligned shared-memory destination
 // TMA-fed layers keep the patch pixel-major instead: 128 bytes (64 channels) per position,
 // 128B-swizzled exactly as a SWIZZLE_128B tensor load of the NHWC source leaves it.
 constexpr int kPatchBytesSw = kPatchPos * 128;  // 43,520
@@ -39,8 +41,30 @@ enum ConvMode : int32_t {
 };
 
 enum OutMode : int32_t {
-  kOutAct = 0,      // 16-bit NHWC activation (+ optional identity residual, + pair statistics)
-  kOutEpsNCHW = 1,  // fp32 NCHW, first `out_c` channels only (final conv)
+  kOutAct = 0,        // 16-bit NHWC activation (+ optional identity residual, + pair statistics)
+  kOutEpsNCHW = 1,    // fp32 NCHW, first `out_c` channels only (final conv -> eps: the fdsr_unet_forward hook)
+  kOutPosterior = 2,  // final conv inside the sampler: eps stays in registers, the epilogue does the whole p_sample
+                      // update (diffusion.py:157-190) on the fp32 x_t state in place and writes the next step's
+                      // 16-bit network input channels (diffusion.py:173) — no eps tensor, no separate kernels
+};
+
+// Per-call arguments of the sampler that live in DEVICE memory, so that one captured CUDA graph per
+// (B, H, W, injected-noise?, trace?) serves every seed, image offset, noise tensor and trace tensor.
+struct SampleArgs {
+  uint64_t seed;         // Philox key
+  uint64_t image0;       // global index of the first image of this batch
+  const float* noise;    // (T,B,3,H,W) injected noise, or null: built-in generator
+  float* trace;          // (B, frames, 3, H, W), or null
+};
+// posterior coefficients of one step (diffusion.py:140-155 tables as fp32, like the reference's registered buffers)
+struct PostCoef {
+  float a, b, c1, c2, sigma;
+};
+struct PostStep {
+  PostCoef k;
+  int32_t z_block;    // block of the injected noise tensor holding this step's z (1 + steps already done)
+  int32_t add_noise;  // 0 for t == 0
+  int32_t pad_[1];
 };
 
 struct ConvChunk {
@@ -85,7 +109,8 @@ struct ConvLayer {
   int32_t ncg;          // 16-byte channel groups per chunk (8, or 2 for the 16-channel stem input)
   int32_t mode;         // ConvMode
   int32_t nG, nR;       // patch stages in ring 0 (full) / ring 1 (centre boxes); nR = 0: single ring
-  int32_t a_tma;        // 1: input patches arrive by TMA (kModeNormal, 64-channel chunks); 0: gathered by the producer warps
+  int32_t a_tma;        // 1: input patches arrive by TMA (kModeNormal, 64-channel chunks); 0: gathered by the producer warps;
+                        // 2: the 16-channel stem input arrives as two 8-channel TMA plane loads (no-swizzle patch layout)
   int32_t B, H, W;      // output size
   int32_t N;            // MMA N of one CTA (16 / 64 / 128 / 256)
   int32_t n_full;       // channel width of the output tensor and of the packed weight blobs (= N * nsplit)
@@ -117,6 +142,11 @@ struct ConvLayer {
                            // grid, every tap position is shifted by (py*kPatchW + px), weights are per phase
   int32_t tiles_x, tiles_y, ntiles;
   int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)
+  // kOutPosterior
+  const PostStep* post;    // [T]
+  float* x_state;          // fp32 NCHW (B,3,H,W): x_t in, x_{t-1} out (in place)
+  void* xin;               // 16-bit NHWC16 network input: channels 0-2 receive x_{t-1}
+  const SampleArgs* args;
   unsigned int* flags;     // context status word: bit 0 = an fp16 activation store saturated (overflow)
   int32_t dbg;             // experiments (tools/): bit0 skip epilogue work, bit1 skip producer work
   long long* prof;         // role cycle counters [grid][4 roles][8 slots] (FDSR_PROFILE builds only)

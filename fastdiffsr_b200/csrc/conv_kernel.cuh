@@ -32,6 +32,7 @@
 #pragma once
 #include "conv_desc.h"
 #include "ptx.cuh"
+#include "sampler_math.cuh"
 
 namespace fdsr {
 
@@ -449,13 +450,14 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // producers gather it, 128B-swizzled pixel-major rows (SBO = 10 positions x 128 B, layout type 2)
     // when TMA delivers it; the hardware swizzle is a function of the absolute shared-memory address
     // (tools/probe_umma.cu layouts 3/4), so a tap is still just a shifted start address.
-    const bool sw = L.a_tma != 0;
+    const bool sw = L.a_tma == 1;
     const uint32_t a_hi_full = sw ? (((kPatchW * 128) >> 4) | (1u << 14) | (2u << 29)) : (((kPatchW * 16) >> 4) | (1u << 14));
     const uint32_t a_hi_cen = ((kTileW * 128) >> 4) | (1u << 14) | (2u << 29);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
     // (inside a cluster, shared-window addresses carry the CTA rank above bit 18: keep the 18-bit offset)
-    const uint32_t a_lo0 = ((sw ? 1u : uint32_t(kPlaneBytes >> 4)) << 16) + ((sA & 0x3FFFFu) >> 4);
-    const uint32_t kstep = sw ? 2u : 2u * kPlanePos;  // 16-byte units between K = 16 slices
+    const uint32_t plane16 = L.a_tma == 2 ? uint32_t(kPlaneBytesTma >> 4) : uint32_t(kPlaneBytes >> 4);
+    const uint32_t a_lo0 = ((sw ? 1u : plane16) << 16) + ((sA & 0x3FFFFu) >> 4);
+    const uint32_t kstep = sw ? 2u : 2u * plane16;  // 16-byte units between K = 16 slices
     const int pos_sh = sw ? 3 : 0;                    // patch position -> 16-byte units
     const uint32_t mt1_full = uint32_t(16 * kPatchW) << pos_sh;  // second 128-row MMA tile: 16 image rows down
     const uint32_t b_lo0 = (uint32_t((NB * 16) >> 4) << 16) + ((sB & 0x3FFFFu) >> 4);
@@ -614,7 +616,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (elect_one()) {
             const ConvChunk& ak = L.chunk[a_c];
             const uint32_t dst = sA + slot_off(a_as);
-            if (ak.gn != 0) {
+            if (L.a_tma == 2) {
+              // 16-channel stem input: two 8-channel planes (box 8 ch x 10 x 34, no swizzle) land as the
+              // [channel group][position][8 ch] patch the gathered layers use; nothing for the producer warps to do
+              const uint32_t bar = bar_a_full(a_as);
+              mbar_arrive_cnt(bar, kProdWarps - 1);
+              mbar_arrive_expect_tx(bar, 2 * kPatchPos * 16);
+              tma_load_4d(&L.in_map[ak.src], dst, bar, ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
+              tma_load_4d(&L.in_map[ak.src], dst + kPlaneBytesTma, bar, ak.c0 + 8, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
+            } else if (ak.gn != 0) {
               mbar_arrive_expect_tx(bar_raw_full(a_as), kPatchBytesSw);
               tma_load_4d(&L.in_map[ak.src], dst, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b >> phsh);
             } else {
@@ -922,6 +932,40 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             }
           }
           PROF_MARK(7);
+        } else if (L.out_mode == kOutPosterior) {
+          // final conv inside the sampler: this thread holds eps of one pixel (3 channels).  p_sample in registers:
+          // x0 = clamp(a x - b eps), mean, + sigma z (z injected or one Philox block keyed by the pixel), fp32 state
+          // updated in place, and the next step's network input rewritten — diffusion.py:157-190, 173
+          if (valid && cb == 0) {
+            const PostStep ps = L.post[t_step];
+            const size_t HWs = size_t(H) * W, o0 = (size_t(b) * 3 * H + y) * W + x;
+            float zv[3] = {0.f, 0.f, 0.f};
+            if (ps.add_noise) {
+              const float* nz = L.args->noise;
+              if (nz != nullptr) {
+                nz += size_t(ps.z_block) * L.B * 3 * HWs;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) zv[c] = nz[o0 + c * HWs];
+              } else {
+                const float4 r4 = philox_normal4(L.args->seed, uint32_t(t_step), L.args->image0 + b, uint32_t(y * W + x));
+                zv[0] = r4.x;
+                zv[1] = r4.y;
+                zv[2] = r4.z;
+              }
+            }
+            float xp[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              xp[c] = post1(L.x_state[o0 + c * HWs], v[c], zv[c], ps.k);
+              L.x_state[o0 + c * HWs] = xp[c];
+            }
+            if constexpr (sizeof(T) == 2) {   // channels [x0 x1 x2 0] of the packed input (pack_input_kernel's layout)
+              uint2 w;
+              w.x = Cvt<T>::pack(xp[0], xp[1]);
+              w.y = Cvt<T>::pack(xp[2], 0.f);
+              *reinterpret_cast<uint2*>(reinterpret_cast<T*>(L.xin) + (size_t(b) * HWs + size_t(y) * W + x) * 16) = w;
+            }
+          }
         } else {  // fp32 NCHW, first out_c channels (final conv -> eps)
           if (valid && cb == 0) {
             float* o = reinterpret_cast<float*>(L.out);

@@ -11,6 +11,11 @@ form and the fp32 reference).
   FDSR_TMA_IN=0      every input patch gathered by the producer warps (which also selects the nine-tap upsample
                      form)                                                           vs  TMA tensor loads
   FDSR_SPLIT_N=0     256-wide low-resolution layers on one CTA per tile              vs  two 128-column halves
+  FDSR_PAIR=0        every layer on single CTAs (tcgen05.mma.cta_group::1)           vs  CTA pairs (cta_group::2, M = 256,
+                     each CTA staging half of the weight columns) where the tile rows are even
+  FDSR_STEM_TMA=0    16-channel stem input gathered by the producer warps           vs  two 8-channel TMA plane loads
+  FDSR_FUSED_TAIL=0  sampler: pack_input / final conv -> eps / posterior kernels    vs  the final conv's epilogue doing the
+                     posterior update in registers and rewriting the next step's input (checked on the sampler)
 """
 import os
 
@@ -53,7 +58,8 @@ def base(oracle, schedule, inputs):
     return eng, eng.unet_forward(inputs[0], inputs[1], 9)
 
 
-@pytest.mark.parametrize("switch,tol", [("FDSR_S2D_TMA", 0.0), ("FDSR_SPLIT_N", 0.0), ("FDSR_RESID_MMA", 3e-3),
+@pytest.mark.parametrize("switch,tol", [("FDSR_S2D_TMA", 0.0), ("FDSR_SPLIT_N", 0.0), ("FDSR_STEM_TMA", 0.0),
+                                        ("FDSR_PAIR", 3e-3), ("FDSR_RESID_MMA", 3e-3),
                                         ("FDSR_UP_PHASES", 3e-3), ("FDSR_TMA_IN", 3e-3)])
 def test_alternative_paths_agree(oracle, schedule, inputs, base, switch, tol):
     eng0, eps0 = base
@@ -63,6 +69,8 @@ def test_alternative_paths_agree(oracle, schedule, inputs, base, switch, tol):
     print(f"{switch}=0 vs default: eps rel-L2 {r:.3e}")
     if tol == 0.0:
         assert torch.equal(eps1, eps0), (switch, r)
+    elif switch == "FDSR_PAIR":
+        assert r <= tol, (switch, r)            # (measured: bit-identical — cta_group::2 accumulates like ::1)
     else:
         assert 0.0 < r <= tol, (switch, r)      # (a zero difference would mean the switch did nothing)
 
@@ -81,3 +89,36 @@ def test_phase_upsample_layers_vs_oracle(oracle, schedule, inputs, base):
         got = eng.read_tensor(name, B, taps[name].numel()).cpu()
         assert got.shape == taps[name].shape
         assert rel_l2(got, taps[name]) <= 5e-3, name
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_fused_tail_equals_separate_kernels(oracle, schedule, dtype):
+    """The sampler with the posterior update fused into the final conv's epilogue (default) equals, bit for bit, the
+    sampler that writes eps, runs posterior_kernel and re-packs the input each step — with injected noise, with the
+    built-in generator, and with the continous=True trace (diffusion.py:157-221)."""
+    from fastdiffsr_b200 import Engine
+    cfg = dict(oracle.DEFAULT_UNET)
+    sd = oracle.make_state_dict(cfg, seed=0, gn_jitter=0.1)
+
+    def mk(env):
+        os.environ.update(env)
+        try:
+            e = Engine(cfg, "cuda:0", dtype)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        e.load_state_dict(sd)
+        e.set_schedule(schedule["betas"])
+        return e
+
+    fused, plain = mk({}), mk({"FDSR_FUSED_TAIL": "0"})
+    g = torch.Generator().manual_seed(31)
+    cond = (torch.rand(3, 3, 64, 96, generator=g) * 2 - 1).cuda()
+    noises = torch.randn(20, 3, 3, 64, 96, generator=g).cuda()
+    a, ta = fused.sample(cond, noise=noises, trace=True)
+    b, tb = plain.sample(cond, noise=noises, trace=True)
+    assert torch.equal(a, b) and torch.equal(ta, tb)
+    assert torch.equal(fused.sample(cond, seed=5, image_offset=7), plain.sample(cond, seed=5, image_offset=7))
+    assert fused.launch_count() < plain.launch_count()      # two launches fewer per step
+    fused.close()
+    plain.close()

@@ -1,5 +1,5 @@
 """A/B timing of library builds on one box in one session (GPU clocks drift by a few % between boxes / runs, so
-small changes can only be judged back to back): python tools/ab_perf.py libA.so libB.so [...] [--reps 3] [--B 16] [--H 256]
+small changes can only be judged back to back): python tools/ab_perf.py libA.so libB.so[@ENV=VAL,...] [...] [--reps 3] [--B 16] [--H 256]
 Prints per build the mean over rounds of (sum of per-op times of one UNet evaluation, T=20 sampling time)."""
 import os
 import subprocess
@@ -24,7 +24,11 @@ while i < len(args):
 res = {l: [] for l in libs}
 for r in range(reps):
     for l in libs:
-        env = dict(os.environ, FDSR_LIB=os.path.abspath(l))
+        path, _, envs = l.partition("@")
+        env = dict(os.environ, FDSR_LIB=os.path.abspath(path))
+        for kv in filter(None, envs.split(",")):
+            k, _, v = kv.partition("=")
+            env[k] = v
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "perf_layers.py"), B, H, dtype], env=env,
                              capture_output=True, text=True).stdout
         ops = [x for x in out.splitlines() if x.startswith("sum of ops")]
@@ -32,7 +36,7 @@ for r in range(reps):
         if ops and smp:
             res[l].append((float(ops[0].split()[3]), float(smp[0].split()[3])))
         if r == reps - 1:
-            open(os.path.join(ROOT, "gpurun_out", "ab_" + os.path.basename(l) + ".log"), "w").write(out)
+            open(os.path.join(ROOT, "gpurun_out", "ab_" + os.path.basename(l).replace("=", "") + ".log"), "w").write(out)
 for l in libs:
     v = res[l]
     if v:
