@@ -155,6 +155,7 @@ struct fdsr_ctx {
   bool tma_in = true;    // FDSR_TMA_IN=0: producer warps gather every input patch (no TMA loads of the A operand)
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
+  bool half_tiles = true;  // FDSR_HALF_TILES=0: 32 x 8 tiles everywhere (the <= 64^2 wide layers then use split-N / single accumulators)
   bool stem_tma = true;  // FDSR_STEM_TMA=0: the 16-channel stem input is gathered by the producer warps
   bool fused_tail = true;  // FDSR_FUSED_TAIL=0: the sampler runs pack_input / final conv -> eps / posterior as separate kernels
   PostStep* d_post = nullptr;      // [T] per-step posterior arguments of the fused final-conv epilogue
@@ -906,7 +907,7 @@ bool make_out_map_phase(CUtensorMap* m, void* ptr, int B, int h, int w, int C, i
 // one load = one 64-channel input patch with halo, pixel-major 128-byte rows, zero-filled outside the image
 // kind 0: full patch; 1: centre box {64, 8, 32}; 2: space-to-depth plane = box {64, 20, 68} traversed with element
 // strides {1, 2, 2, 1} (every second pixel in x and y: 10 x 34 positions land in shared memory)
-bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16, int kind) {
+bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bool bf16, int kind, int tile_h = kTileH) {
   EncodeTiledFn enc = get_encode_tiled();
   if (kind == 3) {  // 16-channel stem input: one 8-channel plane of the patch per load (box {8, 10, 34}), no swizzle
     if (!enc || C != 16) return false;
@@ -922,7 +923,7 @@ bool make_in_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, bo
   const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
   const cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
   const cuuint32_t sc = kind == 2 ? 2 : 1;
-  const cuuint32_t box[4] = {64, cuuint32_t(kind == 1 ? kTileW : kPatchW) * sc, cuuint32_t(kind == 1 ? kTileH : kPatchH) * sc, 1};
+  const cuuint32_t box[4] = {64, cuuint32_t(kind == 1 ? kTileW : kPatchW) * sc, cuuint32_t(kind == 1 ? tile_h : tile_h + 2) * sc, 1};
   const cuuint32_t estr[4] = {1, sc, sc, 1};
   return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1088,12 +1089,22 @@ int upload_layers(fdsr_ctx* c) {
     l.H = (H >> lvl) >> (k.phases == 4 ? 1 : 0);
     l.W = (W >> lvl) >> (k.phases == 4 ? 1 : 0);
     l.tiles_x = (l.W + kTileW - 1) / kTileW;
-    l.tiles_y = (l.H + kTileH - 1) / kTileH;
+    // Half tiles (16 x 8 pixels, one MMA tile per CTA tile), run as CTA pairs, for the wide layers whose 32 x 8 tiles
+    // would not fill the GPU (32^2 at B = 16: 64 tiles; everything below 256^2 at B = 1): twice the CTAs, half the patch
+    // each CTA loads and normalises, and N = 256 gets a second TMEM accumulator stage.  The weight bytes per pixel double,
+    // which is why layers with enough full tiles keep them (64^2 at B = 16: measured 1.3 % slower per step as half tiles).
+    // Results are bit-identical for either shape (per-warp statistics are added as integers), so the choice may follow B.
+    const bool tma_normal = c->tma_in && k.mode == kModeNormal && k.ncg == 8;
+    const int full_tiles = B * l.tiles_x * ((l.H + kTileH - 1) / kTileH);
+    const bool half = c->half_tiles && c->pair && tma_normal && k.phases == 1 && k.out_mode == kOutAct && k.N >= 128 &&
+                      l.tiles_x % 2 == 0 && l.H % 16 == 0 && full_tiles <= c->num_sms;
+    l.tile_h = half ? 16 : kTileH;
+    l.tiles_y = (l.H + l.tile_h - 1) / l.tile_h;
     l.ntiles = B * k.phases * l.tiles_x * l.tiles_y;
     // Split-N: a low-resolution layer with fewer 256-pixel tiles than half the SMs is computed as two
     // 128-column halves by twice as many CTAs.  Only 256 -> 2 x 128: both widths use the same
     // per-tile statistics path, so results stay bitwise independent of the batch size.
-    l.nsplit = (c->split_n && k.out_mode == kOutAct && k.N == 256 &&
+    l.nsplit = (!half && c->split_n && k.out_mode == kOutAct && k.N == 256 &&
                 (2 * l.ntiles <= c->num_sms || c->split_all)) ? 2 : 1;
     l.n_full = k.N;
     l.N = k.N / l.nsplit;
@@ -1114,10 +1125,11 @@ int upload_layers(fdsr_ctx* c) {
       l.a_tma = 2;  // the stem: two 8-channel TMA plane loads per tile, no producer work
     for (int s = 0; s < k.nsrc && l.a_tma == 1; ++s)
       if (!make_in_map(&l.in_map[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
-                       c->cfg.dtype == FDSR_DTYPE_BF16, 0) ||
+                       c->cfg.dtype == FDSR_DTYPE_BF16, 0, l.tile_h) ||
           !make_in_map(&l.in_map_c[s], l.src[s].ptr, B, l.src[s].H, l.src[s].W, l.src[s].C,
-                       c->cfg.dtype == FDSR_DTYPE_BF16, s2d_tma ? 2 : 1))
+                       c->cfg.dtype == FDSR_DTYPE_BF16, s2d_tma ? 2 : 1, l.tile_h))
         l.a_tma = 0;
+    if (half && l.a_tma != 1) return fail(c, FDSR_E_CUDA, "layer %s: tensor maps of the half-tile form failed", k.name.c_str());
     l.nchunks = int(k.chunks.size());
     int any_center = 0;
     size_t woff = 0;
@@ -1575,6 +1587,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tma_store = !(e2 && e2[0] == '0');
     const char* e3 = getenv("FDSR_PAIR");
     c->pair = !(e3 && e3[0] == '0');
+    const char* e15 = getenv("FDSR_HALF_TILES");
+    c->half_tiles = !(e15 && e15[0] == '0');
     const char* e13 = getenv("FDSR_STEM_TMA");
     c->stem_tma = !(e13 && e13[0] == '0');
     const char* e14 = getenv("FDSR_FUSED_TAIL");

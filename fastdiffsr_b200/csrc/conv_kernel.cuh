@@ -63,6 +63,7 @@ struct ConvCfg {
   static constexpr int kAccStride = N < 32 ? 32 : N;        // TMEM columns per 128-row accumulator
   static constexpr int kAccCols = 2 * kAccStride;           // two MMA tiles per CTA tile
   static constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;
+  static constexpr int kNumAccMax = 2;  // half tiles (one MMA tile per CTA tile) double-buffer N = 256 as well
   // N = 64: per-lane running GroupNorm sums live in TMEM columns [256, 384)
   static constexpr bool kStatsInTmem = (N == 64);
   static constexpr int kStatCol0 = kNumAcc * kAccCols;
@@ -111,7 +112,7 @@ struct ConvCfg {
   static constexpr int kOffTstat = kOffBias + 256 * 4;
   static constexpr int kOffBar = kOffTstat + kEpiWarps * kRow * 4;  // one row of pair sums per epilogue warp
   // (+ the pair-mode relay barriers: the peer CTA's a_full / b_full / acc_empty as seen by the leader's MMA warp)
-  static constexpr int kNumBar = 3 * kASlots + 2 * kBStages + 2 * kNumAcc + (kASlots + kBStages + kNumAcc);
+  static constexpr int kNumBar = 3 * kASlots + 2 * kBStages + 2 * kNumAccMax + (kASlots + kBStages + kNumAccMax);
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   // per-epilogue-warp 2 KB staging block for the TMA store of 32 px x 32 ch (64B-swizzled)
   static constexpr int kOffStage = ((kOffTmem + 16 + 1023) / 1024) * 1024;
@@ -346,13 +347,13 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   auto bar_b_empty = [&](int s) { return bar0 + 8u * (2 * kASlots + Cfg::kBStages + s); };
   auto bar_acc_full = [&](int s) { return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + s); };
   auto bar_acc_empty = [&](int s) {
-    return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + Cfg::kNumAcc + s);
+    return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + Cfg::kNumAccMax + s);
   };
   auto bar_raw_full = [&](int s) {  // TMA-fed layers: the raw patch of stage s has landed
-    return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + 2 * Cfg::kNumAcc + s);
+    return bar0 + 8u * (2 * kASlots + 2 * Cfg::kBStages + 2 * Cfg::kNumAccMax + s);
   };
   // pair-mode relay barriers (used in the leader CTA only; arrivals come from the peer's warp 0)
-  constexpr int kBarRelay0 = 3 * kASlots + 2 * Cfg::kBStages + 2 * Cfg::kNumAcc;
+  constexpr int kBarRelay0 = 3 * kASlots + 2 * Cfg::kBStages + 2 * Cfg::kNumAccMax;
   auto bar_pa_full = [&](int s) { return bar0 + 8u * (kBarRelay0 + s); };
   auto bar_pb_full = [&](int s) { return bar0 + 8u * (kBarRelay0 + kASlots + s); };
   auto bar_pacc_empty = [&](int s) { return bar0 + 8u * (kBarRelay0 + kASlots + Cfg::kBStages + s); };
@@ -373,7 +374,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       mbar_init(bar_b_empty(s), 1);
       mbar_init(bar_pb_full(s), 1);
     }
-    for (int s = 0; s < Cfg::kNumAcc; ++s) {
+    for (int s = 0; s < Cfg::kNumAccMax; ++s) {
       mbar_init(bar_acc_full(s), 1);
       mbar_init(bar_acc_empty(s), kEpiWarps);
       mbar_init(bar_pacc_empty(s), 1);
@@ -426,6 +427,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   const int tile_end = tile_begin + my_units * tgroup;
   const int tile_first = tile_begin * kTStep + int(crank);  // index of this CTA's first tile in the layer's tile order
   const int tiles_per_img = L.tiles_x * L.tiles_y;
+  // Tile shape.  Full tiles are 32 x 8 pixels = two 128-row MMA tiles sharing every weight stage.  Half tiles (16 x 8, one
+  // MMA tile; low-resolution N >= 128 layers run as CTA pairs): twice the CTAs per layer, half the patch to load and
+  // normalise per CTA, and the accumulator takes N instead of 2N TMEM columns, so that N = 256 is double-buffered too.
+  const int TH = L.tile_h;
+  const bool two_mt = TH == kTileH;
+  const int npos = (TH + 2) * kPatchW;                        // patch positions (340 / 180)
+  const uint32_t patch_bytes = uint32_t(npos) * 128u, cen_bytes = uint32_t(TH) * kTileW * 128u;
+  const int nacc = two_mt ? Cfg::kNumAcc : Cfg::kNumAccMax;   // accumulator stages
+  const uint32_t acc_cols = two_mt ? Cfg::kAccCols : Cfg::kAccStride;  // TMEM columns per stage
   const int ncg = L.ncg;
   const uint32_t blob = uint32_t(ncg) * NB * 16;  // bytes of one tap's weight blob (the columns this CTA stages)
   const uint32_t gblob = uint32_t(ncg) * uint32_t(n_full) * 16;  // split-N: the same tap in global memory (all columns)
@@ -487,7 +497,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       pair_sync(bar_pacc_empty(acc), accph);
       PROF_MARK(0);
       tc_fence_after();
-      const uint32_t d0 = tmem + acc * Cfg::kAccCols;
+      const uint32_t d0 = tmem + acc * acc_cols;
       const uint32_t phoff = L.phases > 1 ? uint32_t(((m_bv >> 1) & 1) * kPatchW + (m_bv & 1)) << pos_sh : 0u;
       if ((m_tin += kTStep) >= tiles_per_img) { m_tin -= tiles_per_img; ++m_bv; }
       for (int c = 0; c < L.nchunks; ++c) {
@@ -525,10 +535,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                 const uint64_t ad1 = (uint64_t(a_hi) << 32) | (a_lo + ks * kstep + mt1);
                 if constexpr (kPair) {
                   umma_f16_pair(d0, ad0, bd, idesc, ks ? 1u : accum0);
-                  umma_f16_pair(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
+                  if (two_mt) umma_f16_pair(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
                 } else {
                   umma_f16(d0, ad0, bd, idesc, ks ? 1u : accum0);
-                  umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
+                  if (two_mt) umma_f16(d0 + Cfg::kAccStride, ad1, bd, idesc, ks ? 1u : accum0);
                 }
               };
               if (ksteps == 4) {
@@ -564,7 +574,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (++gs == nG) { gs = 0; gph ^= 1; }
         }
       }
-      if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
+      if (++acc == nacc) { acc = 0; accph ^= 1; }
     }
     if (lane == 0) PROF_FLUSH(0);
   } else if (warp == 1) {
@@ -625,21 +635,21 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
               tma_load_4d(&L.in_map[ak.src], dst, bar, ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
               tma_load_4d(&L.in_map[ak.src], dst + kPlaneBytesTma, bar, ak.c0 + 8, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b);
             } else if (ak.gn != 0) {
-              mbar_arrive_expect_tx(bar_raw_full(a_as), kPatchBytesSw);
-              tma_load_4d(&L.in_map[ak.src], dst, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b >> phsh);
+              mbar_arrive_expect_tx(bar_raw_full(a_as), patch_bytes);
+              tma_load_4d(&L.in_map[ak.src], dst, bar_raw_full(a_as), ak.c0, a_tx * kTileW - 1, a_ty * TH - 1, a_b >> phsh);
             } else {
               const uint32_t bar = bar_a_full(a_as);
               mbar_arrive_cnt(bar, kProdWarps - 1);  // stands in for the producer warps
               if (L.mode == kModeS2D) {  // parity plane (pa, pb) of the stride-2 conv's input: every second pixel
-                mbar_arrive_expect_tx(bar, kPatchBytesSw);
+                mbar_arrive_expect_tx(bar, patch_bytes);
                 tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, 2 * (a_tx * kTileW - 1) + (ak.parity & 1),
-                            2 * (a_ty * kTileH - 1) + (ak.parity >> 1), a_b);
+                            2 * (a_ty * TH - 1) + (ak.parity >> 1), a_b);
               } else if (ak.center != 0) {
-                mbar_arrive_expect_tx(bar, kTileH * kTileW * 128);
-                tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, a_tx * kTileW, a_ty * kTileH, a_b >> phsh);
+                mbar_arrive_expect_tx(bar, cen_bytes);
+                tma_load_4d(&L.in_map_c[ak.src], dst, bar, ak.c0, a_tx * kTileW, a_ty * TH, a_b >> phsh);
               } else {
-                mbar_arrive_expect_tx(bar, kPatchBytesSw);
-                tma_load_4d(&L.in_map[ak.src], dst, bar, ak.c0, a_tx * kTileW - 1, a_ty * kTileH - 1, a_b >> phsh);
+                mbar_arrive_expect_tx(bar, patch_bytes);
+                tma_load_4d(&L.in_map[ak.src], dst, bar, ak.c0, a_tx * kTileW - 1, a_ty * TH - 1, a_b >> phsh);
               }
             }
           }
@@ -712,7 +722,10 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // =========================================================== epilogue
     const int ew = warp - 4;           // 0..7
     const int q = ew & 3;              // TMEM lane quarter owned by this warp (== warp % 4)
-    const int mt = ew >> 2;            // which 128-row MMA tile of the CTA tile
+    // full tiles: one warpgroup per 128-row MMA tile; half tiles: both warpgroups drain the one MMA tile, warpgroup h
+    // taking the 32-column blocks with (cb & 1) == h (a warp may only touch the TMEM lane quarter warp % 4)
+    const int mt = two_mt ? ew >> 2 : 0;
+    const int cb_first = two_mt ? 0 : (ew >> 2), cb_step = two_mt ? 1 : 2;
     const int et = tid - 128;          // 0..255
     const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride + n_off;
     for (int i = et; i < kRow; i += kEpiThreads) bias_s[i] = i < N ? bias_g[i] : 0.f;
@@ -745,7 +758,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     float vmax = 0.f;
     PROF_DECL;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int x = tx * kTileW + r, y = ty * kTileH + mt * 16 + g;
+      const int x = tx * kTileW + r, y = ty * TH + mt * 16 + g;
       const bool valid = y < H && x < W;
       const bool all_valid = __all_sync(0xffffffffu, valid);
       // phase layers: b is a virtual image (image * 4 + py * 2 + px) and (y, x) a low-resolution position whose output
@@ -759,7 +772,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       uint4 rq[4];  // identity residual of the next 32 channels, fetched before it is needed
       if (has_res) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + k, valid);
+        for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + cb_first * 4 + k, valid);
         // pull this lane's residual row of the NEXT tile into L2 while this tile is drained (the loads
         // above then mostly hit L2 instead of exposing HBM latency on the epilogue's critical path)
         int ntx = tx + kTStep, nty = ty, nb = b;
@@ -767,7 +780,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           ntx -= tiles_x;
           if (++nty == L.tiles_y) { nty = 0; ++nb; }
         }
-        const int nx = ntx * kTileW + r, ny = nty * kTileH + mt * 16 + g;
+        const int nx = ntx * kTileW + r, ny = nty * TH + mt * 16 + g;
         if (tile + 1 < tile_end && ny < H && nx < W) {
           const uint8_t* np = reinterpret_cast<const uint8_t*>(L.resid) +
                               (size_t(uint32_t((nb * H + ny) * W + nx)) * n_full + n_off) * 2;
@@ -778,9 +791,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       mbar_wait(bar_acc_full(acc), accph);
       PROF_MARK(0);
       tc_fence_after();
-      const uint32_t taddr = lane_base + acc * Cfg::kAccCols + mt * Cfg::kAccStride;
+      const uint32_t taddr = lane_base + acc * acc_cols + mt * Cfg::kAccStride;
 #pragma unroll 1
-      for (int cb = 0; cb < ((L.dbg & 1) ? 0 : Cfg::kNcb); ++cb) {
+      for (int cb = cb_first; cb < ((L.dbg & 1) ? 0 : Cfg::kNcb); cb += cb_step) {
         uint32_t raw[32];
         tmem_ld32(taddr + cb * 32, raw);
         tmem_ld_wait();
@@ -807,9 +820,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
                 v[k * 8 + e * 2 + 1] += f.y;
               }
             }
-            if (cb + 1 < Cfg::kNcb) {
+            if (cb + cb_step < Cfg::kNcb) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + (cb + 1) * 4 + k, valid);
+              for (int k = 0; k < 4; ++k) rq[k] = ldg16_pred(rp + (cb + cb_step) * 4 + k, valid);
             }
           }
           if constexpr (kOverflowCheck) {  // largest magnitude about to be stored as fp16 (one FMNMX3 per two values)
@@ -841,7 +854,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             __syncwarp();
             if (lane == 0) {
               tma_store_4d(ph == 0 ? &L.out_map : &L.out_map_ph[ph - 1], stage_s, n_off + cb * 32, tx * kTileW,
-                           ty * kTileH + mt * 16 + q * 4, b_img);
+                           ty * TH + mt * 16 + q * 4, b_img);
               bulk_commit_group();
             }
           } else if (valid && !(L.dbg & 4)) {
@@ -980,7 +993,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty(acc));
       PROF_MARK(1);
-      if (++acc == Cfg::kNumAcc) { acc = 0; accph ^= 1; }
+      if (++acc == nacc) { acc = 0; accph ^= 1; }
       // next tile coordinates (no divisions in the loop)
       const int b_cur = b_img;
       if ((tx += kTStep) >= tiles_x) {
@@ -1010,13 +1023,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           // warps in fixed order, then order-independent 64-bit fixed-point atomics: the statistics
           // (and therefore every activation) are bitwise reproducible run to run
           named_bar_sync(2, kEpiThreads);
+          // every warp total is converted to fixed point BEFORE the warps are added: integer addition is associative, so
+          // the CTA's contribution does not depend on how the same 32-pixel warp blocks are grouped into tiles (full / half
+          // tiles, split-N) — the tile shape may follow the batch size without changing a single bit of the result
           for (int i = et; i < N; i += kEpiThreads) {
-            float tsum = 0.f;
+            const float sc = (i & 1) ? L.out_sq_scale : float(kStatScale);  // entry layout [pair][2]: sum, sum of squares
+            long long tsum = 0;
 #pragma unroll
-            for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += tstat[w8 * kRow + i];
-            // entry layout [pair][2]: even = sum, odd = sum of squares
-            atomicAdd(L.out_stats + size_t(b_cur) * n_full + n_off + i,
-                      static_cast<unsigned long long>(__float2ll_rn(tsum * ((i & 1) ? L.out_sq_scale : float(kStatScale)))));
+            for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += __float2ll_rn(tstat[w8 * kRow + i] * sc);
+            atomicAdd(L.out_stats + size_t(b_cur) * n_full + n_off + i, static_cast<unsigned long long>(tsum));
           }
           named_bar_sync(2, kEpiThreads);
         }
@@ -1105,7 +1120,9 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       // (stage s starts 341 s = 5 s mod 8 rows into the swizzle period)
       const int pos0 = pidx >> 3;
       const int py0 = pos0 / kPatchW, px0 = pos0 - py0 * kPatchW;  // position of unit i: (py0 + 4 i, px0)
-      const uint32_t smask = pos0 < kPatchPos - 8 * 40 ? 0x1ffu : 0xffu;
+      uint32_t smask = 0u;  // unit i = position pos0 + 40 i exists in the (TH + 2) x 10 patch
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i) smask |= (pos0 + 40 * i < npos) ? (1u << i) : 0u;
       uint32_t rph = 0u;  // bit s: parity of the next phase of raw_full(s) (only GroupNorm chunks use it)
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         if (L.gn_C > 0 && b != cur_b) {
@@ -1114,7 +1131,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           if (pidx == 0 && tile == tile_begin) PROF_TS(2);  // GroupNorm table of the first image built
         }
         // units inside the image (padding must stay zero: swish(GN(0)) != 0)
-        const int y0 = ty * kTileH - 1 + py0, x0 = tx * kTileW - 1 + px0;
+        const int y0 = ty * TH - 1 + py0, x0 = tx * kTileW - 1 + px0;
         uint32_t vmask = 0u;
         if (unsigned(x0) < unsigned(W)) {
 #pragma unroll
