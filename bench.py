@@ -74,17 +74,20 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes (read + write) of the heaviest conv launch (ups.7, 309 GFLOP) from the committed
-    `ncu --set full` capture; the other captured launches are listed in profiles/r1/traffic.json."""
-    p = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    """DRAM bytes (read + write) of the heaviest conv launch (ups.7, 309 GFLOP algorithmic) from the committed
+    `ncu --set full` capture; the other captured launches are listed in profiles/r2/traffic.json."""
+    p = os.path.join(ROOT, "profiles", "r2", "traffic.json")
     try:
         d = json.load(open(p))["launches"]
-        top = d["ups.7"]
+        top = next(v for k, v in d.items() if k.startswith("ups.7"))
+        mb = lambda key: next(x["value"] * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[x["unit"]]
+                              for h, x in top.items() if h.startswith(key))
         note = "ncu dram__bytes_read.sum + dram__bytes_write.sum of launch ups.7 (B=16, 256^2; algorithmic 169 MB: " \
-               "34 MB in + 134 MB out + 1.2 MB weights); per-launch figures for 4 captured launches in profiles/r1/traffic.json"
-        return top["dram_read_bytes"] + top["dram_write_bytes"], note
+               "34 MB in + 134 MB out + 1.2 MB weights; part of the output is still in L2 when the launch ends); per-launch " \
+               "figures for 5 captured launches in profiles/r2/traffic.json"
+        return mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum"), note
     except Exception:
-        return None, "profiles/r1/traffic.json missing"
+        return None, "profiles/r2/traffic.json missing"
 
 
 class ClockSampler:
