@@ -155,6 +155,7 @@ struct fdsr_ctx {
   bool tma_in = true;    // FDSR_TMA_IN=0: producer warps gather every input patch (no TMA loads of the A operand)
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
+  bool epi2 = true;        // FDSR_EPI2=0: producer-free layers keep one epilogue team (warps 4..11)
   bool half_tiles = true;  // FDSR_HALF_TILES=0: 32 x 8 tiles everywhere (the <= 64^2 wide layers then use split-N / single accumulators)
   bool stem_tma = true;  // FDSR_STEM_TMA=0: the 16-channel stem input is gathered by the producer warps
   bool fused_tail = true;  // FDSR_FUSED_TAIL=0: the sampler runs pack_input / final conv -> eps / posterior as separate kernels
@@ -1151,7 +1152,10 @@ int upload_layers(fdsr_ctx* c) {
     }
     // patch rings (see ConvCfg): N = 64 layers with 1x1-residual chunks use 2 full + 2 centre-box stages
     // (with three or more centre boxes per tile two 32 KB stages stall on the third: measured slower)
-    l.nR = (c->two_rings && any_center >= 1 && any_center <= 2 && l.N == 64) ? 2 : 0;
+    {
+      static const int max_center = [] { const char* e = getenv("FDSR_RINGS_MAXC"); return e ? atoi(e) : 2; }();
+      l.nR = (c->two_rings && any_center >= 1 && any_center <= max_center && l.N == 64) ? 2 : 0;
+    }
     l.nG = l.nR ? 2 : (l.N >= 256 ? 2 : 3);
     for (int j = 0; j < l.nchunks; ++j) l.chunk[j].ring = (l.nR && l.chunk[j].center) ? 1 : 0;
     l.gn_C = k.gn_C;
@@ -1201,6 +1205,19 @@ int upload_layers(fdsr_ctx* c) {
       // running TMEM statistics exist for N = 64 only; the group size must not depend on B.  A CTA's consecutive tiles
       // are t, t+1 (single) or t, t+2 (pair): both of a group must belong to one image
       l.group = (l.N == 64 && tpi % (l.pair ? 4 : 2) == 0) ? 2 : 1;
+    }
+    {  // second epilogue team (warps 12..19) for layers whose producer warps have nothing to do
+      // (not the stride-2 convs: they stream four parity-plane chunks per tile and lose more from giving up the third
+      //  patch stage than they gain — measured 49.6 -> 58.8 us for downs.3)
+      bool raw = l.a_tma != 0 && k.mode == kModeNormal && k.out_mode == kOutAct && l.use_tma_store && l.tile_h == kTileH &&
+                 l.nsplit == 1 && k.resid < 0;
+      for (const HChunk& ch : k.chunks) raw = raw && ch.gn == 0;
+      l.epi2 = (c->epi2 && raw) ? 1 : 0;
+      if (l.epi2 && l.N <= 128) {  // their staging blocks live in the third patch stage
+        l.nG = 2;
+        l.nR = 0;
+        for (int j = 0; j < l.nchunks; ++j) l.chunk[j].ring = 0;
+      }
     }
     l.prof = c->d_prof;
     l.flags = reinterpret_cast<unsigned int*>(c->d_ws + kOffFlags);
@@ -1587,6 +1604,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tma_store = !(e2 && e2[0] == '0');
     const char* e3 = getenv("FDSR_PAIR");
     c->pair = !(e3 && e3[0] == '0');
+    const char* e16 = getenv("FDSR_EPI2");
+    c->epi2 = !(e16 && e16[0] == '0');
     const char* e15 = getenv("FDSR_HALF_TILES");
     c->half_tiles = !(e15 && e15[0] == '0');
     const char* e13 = getenv("FDSR_STEM_TMA");

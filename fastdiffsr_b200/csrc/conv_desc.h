@@ -140,6 +140,8 @@ struct ConvLayer {
   int32_t w_half;          //    layout, CTA r of a pair reads from weights + r * w_half
   int32_t phases;          // 1, or 4: tiles run over virtual images (image * 4 + phase), H/W are the low-resolution
                            // grid, every tap position is shifted by (py*kPatchW + px), weights are per phase
+  int32_t epi2;            // 1: layers without producer work (every chunk raw, patches by TMA: up / down-sampling convs,
+                           //    stem) turn producer warps 12..19 into a second epilogue team (odd 32-column blocks)
   int32_t tile_h;          // output rows per CTA tile: 32 (two 128-row MMA tiles) or 16 (one: "half tiles", see upload_layers)
   int32_t tiles_x, tiles_y, ntiles;
   int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)

@@ -116,7 +116,9 @@ struct ConvCfg {
   static constexpr int kOffTmem = kOffBar + kNumBar * 8;
   // per-epilogue-warp 2 KB staging block for the TMA store of 32 px x 32 ch (64B-swizzled)
   static constexpr int kOffStage = ((kOffTmem + 16 + 1023) / 1024) * 1024;
-  static constexpr int kSmemBytes = kOffStage + (N < 32 ? 0 : kEpiWarps * 2048);
+  // (N = 256: + 7 staging blocks of the second epilogue team, whose eighth block is the unused GroupNorm table)
+  static constexpr int kSmemBytes = kOffStage + (N < 32 ? 0 : kEpiWarps * 2048) + (N >= 256 ? 7 * 2048 : 0);
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 };
 
 template <typename T>
@@ -376,7 +378,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     }
     for (int s = 0; s < Cfg::kNumAccMax; ++s) {
       mbar_init(bar_acc_full(s), 1);
-      mbar_init(bar_acc_empty(s), kEpiWarps);
+      mbar_init(bar_acc_empty(s), L.epi2 ? 2 * kEpiWarps : kEpiWarps);
       mbar_init(bar_pacc_empty(s), 1);
     }
     mbar_init_fence();
@@ -401,7 +403,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   if (tid == 0) PROF_TS(0);  // prologue done (barriers, TMEM)
   asm volatile("griddepcontrol.launch_dependents;");
   // (the loader and the producer warps first fetch constants — weights, GroupNorm gamma / beta — and wait in their roles)
-  const bool is_producer = warp == 2 || warp == 3 || warp >= 4 + kEpiWarps;
+  const bool epi_team2 = L.epi2 != 0 && warp >= 4 + kEpiWarps;  // (layers without producer work)
+  const bool is_producer = (warp == 2 || warp == 3 || warp >= 4 + kEpiWarps) && !epi_team2;
   if (warp != 1 && !is_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid == 0) PROF_TS(1);  // previous launch complete
 
@@ -718,26 +721,41 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       }
       if (!progress) __nanosleep(32);
     }
-  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+  } else if ((warp >= 4 && warp < 4 + kEpiWarps) || epi_team2) {
     // =========================================================== epilogue
-    const int ew = warp - 4;           // 0..7
+    // Team 0 = warps 4..11.  Layers whose producer warps have nothing to do (L.epi2: every chunk raw and TMA-fed — these
+    // layers are short on MMAs per tile and bound by this role) add warps 12..19 as team 1: the same (lane quarter, MMA
+    // tile) assignment, the odd 32-column blocks, their own staging blocks, the same statistics rows.
+    const int team = epi_team2 ? 1 : 0;
+    const int nteams = L.epi2 ? 2 : 1, nepi = nteams * kEpiThreads;
+    const int ew = team ? warp - (4 + kEpiWarps) : warp - 4;   // 0..7
     const int q = ew & 3;              // TMEM lane quarter owned by this warp (== warp % 4)
     // full tiles: one warpgroup per 128-row MMA tile; half tiles: both warpgroups drain the one MMA tile, warpgroup h
     // taking the 32-column blocks with (cb & 1) == h (a warp may only touch the TMEM lane quarter warp % 4)
     const int mt = two_mt ? ew >> 2 : 0;
-    const int cb_first = two_mt ? 0 : (ew >> 2), cb_step = two_mt ? 1 : 2;
-    const int et = tid - 128;          // 0..255
+    const int cb_first = two_mt ? team : (ew >> 2), cb_step = two_mt ? nteams : 2;
+    const int et = team ? kEpiThreads + (tid - 32 * (4 + kEpiWarps)) : tid - 128;          // 0..255 (team 0), 256..511
     const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride + n_off;
-    for (int i = et; i < kRow; i += kEpiThreads) bias_s[i] = i < N ? bias_g[i] : 0.f;
-    for (int i = et; i < kEpiWarps * kRow; i += kEpiThreads) tstat[i] = 0.f;
-    named_bar_sync(2, kEpiThreads);
+    for (int i = et; i < kRow; i += nepi) bias_s[i] = i < N ? bias_g[i] : 0.f;
+    for (int i = et; i < kEpiWarps * kRow; i += nepi) tstat[i] = 0.f;
+    named_bar_sync(2, nepi);
     const int su = L.out_su;  // channel pairs per statistics entry (1, 2, 4 or 8)
     const int m = q * 32 + lane, g = m >> 3, r = m & 7;
     const bool act = L.out_mode == kOutAct;
     const bool do_stats = (L.out_stats != nullptr) && act;
     const bool has_res = (L.resid != nullptr) && act;
     const bool use_tma = (N >= 32) && act && L.use_tma_store != 0;
-    const uint32_t stage_s = smem_u32(smem + Cfg::kOffStage) + uint32_t(ew) * 2048;
+    // staging blocks (2 KB, 512-byte aligned for the 64B swizzle).  Team 1: the third patch stage, which a producer-free
+    // layer does not use (N <= 128); N = 256 has only two: the tail of the allocation + the unused GroupNorm table
+    uint32_t stage_s = smem_u32(smem + Cfg::kOffStage) + uint32_t(ew) * 2048;
+    if (team) {
+      if constexpr (N >= 256) {
+        stage_s = ew < 7 ? smem_u32(smem + Cfg::kOffStage) + uint32_t(kEpiWarps + ew) * 2048
+                         : ((smem_u32(smem + Cfg::kOffTable) + 511u) & ~511u);
+      } else {
+        stage_s = ((smem_u32(smem + Cfg::kOffA) + 2u * kAStageBytes + 511u) & ~511u) + uint32_t(ew) * 2048;
+      }
+    }
     const int H = L.H, W = L.W, tiles_x = L.tiles_x;
     const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
     const uint32_t run_addr = lane_base + Cfg::kStatCol0 + mt * N;  // running sums (kStatsInTmem)
@@ -745,7 +763,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       uint32_t z[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) z[j] = 0u;
-      for (int cb = 0; cb < Cfg::kNcb; ++cb) tmem_st32(run_addr + cb * 32, z);
+      for (int cb = cb_first; cb < Cfg::kNcb; cb += cb_step) tmem_st32(run_addr + cb * 32, z);
       tmem_st_wait();
     }
     int acc = 0, accph = 0;
@@ -1004,7 +1022,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
         const bool flush = !Cfg::kStatsInTmem || (tile + 1) % tgroup == 0;
         if (flush) {
           if (Cfg::kStatsInTmem) {
-            for (int cb = 0; cb < Cfg::kNcb; ++cb) {
+            for (int cb = cb_first; cb < Cfg::kNcb; cb += cb_step) {
               uint32_t run[32];
               float fv[32];
               tmem_ld32(run_addr + cb * 32, run);
@@ -1022,18 +1040,18 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           }
           // warps in fixed order, then order-independent 64-bit fixed-point atomics: the statistics
           // (and therefore every activation) are bitwise reproducible run to run
-          named_bar_sync(2, kEpiThreads);
+          named_bar_sync(2, nepi);
           // every warp total is converted to fixed point BEFORE the warps are added: integer addition is associative, so
           // the CTA's contribution does not depend on how the same 32-pixel warp blocks are grouped into tiles (full / half
           // tiles, split-N) — the tile shape may follow the batch size without changing a single bit of the result
-          for (int i = et; i < N; i += kEpiThreads) {
+          for (int i = et; i < N; i += nepi) {
             const float sc = (i & 1) ? L.out_sq_scale : float(kStatScale);  // entry layout [pair][2]: sum, sum of squares
             long long tsum = 0;
 #pragma unroll
             for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += __float2ll_rn(tstat[w8 * kRow + i] * sc);
             atomicAdd(L.out_stats + size_t(b_cur) * n_full + n_off + i, static_cast<unsigned long long>(tsum));
           }
-          named_bar_sync(2, kEpiThreads);
+          named_bar_sync(2, nepi);
         }
       }
       PROF_MARK(2);
@@ -1042,6 +1060,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     if (lane == 0) bulk_wait_all0();  // outstanding bulk tensor stores of this warp
     if (et == 0) PROF_TS(6);  // epilogue of the last tile done, stores complete
     if (et == 0) PROF_FLUSH(1);
+    (void)et;
   } else {
     // =========================================================== input producers
     const int pw = warp < 4 ? warp - 2 : warp - 10;  // warps 2,3,12..19 -> 0..9
