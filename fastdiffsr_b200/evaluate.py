@@ -141,7 +141,7 @@ def main(argv=None, default_config="config/sr_fastdiffsr_test_64_256.json", prog
     ap.add_argument('--batch', type=int, default=16, help='images per GPU per sampling call (reference: 1)')
     ap.add_argument('--no-save', action='store_true', help='do not write SR images')
     ap.add_argument('--max-images', type=int, default=None)
-    ap.add_argument('--dtype', default=os.environ.get("FDSR_DTYPE", "fp16"))
+    ap.add_argument('--dtype', default=os.environ.get("FDSR_DTYPE", "auto"), choices=["auto", "fp16", "bf16", "fp32"])
     args = ap.parse_args(argv)
     if args.phase == 'train':
         raise NotImplementedError("training is outside the B200 sampling path: train with the reference and point "

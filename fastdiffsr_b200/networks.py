@@ -20,7 +20,9 @@ def define_G(opt):
                  inner_channel=u["inner_channel"], channel_mults=u["channel_multiplier"], attn_res=u["attn_res"],
                  res_blocks=u["res_blocks"], dropout=u["dropout"], image_size=model_opt["diffusion"]["image_size"])
     dtype = model_opt.get("compute_dtype") if hasattr(model_opt, "get") else None
-    dtype = dtype or os.environ.get("FDSR_DTYPE", "fp16")
+    # "auto" (default): fp16 — the most accurate 16-bit mode, ~2 % faster than bf16 — until an activation is reported to
+    # leave the fp16 range (a trained network's un-normalised residual stream can), then bf16 storage for good
+    dtype = dtype or os.environ.get("FDSR_DTYPE", "auto")
     netG = GaussianDiffusion(model, image_size=model_opt["diffusion"]["image_size"],
                              channels=model_opt["diffusion"]["channels"], loss_type="l1",
                              conditional=model_opt["diffusion"]["conditional"],
