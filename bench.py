@@ -252,7 +252,27 @@ def run_ours(args, rank, world, local_rank):
         clocks.start()
     ms_dev, launches = timed(step_device, args.steps, max(args.warmup, 3))
     ws_gib = eng.workspace_bytes() / 2 ** 30
-    ms_e2e, _ = timed(step_host, max(2, min(args.steps, 5)), 1)
+    # end to end through the host-buffer API, one batch submitted ahead: the H2D / D2H copies and the host-side memcpy of
+    # batch i overlap the sampling of batch i+1 (every step still copies its own input in and its own result out)
+    def timed_e2e(steps, warmup):
+        for i in range(warmup):
+            step_host(i)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.super_resolve_u8_submit(0, lr_host, H, H, seed=2000, image_offset=first_image)
+        for i in range(1, steps):
+            eng.super_resolve_u8_submit(i % 2, lr_host, H, H, seed=2000 + i, image_offset=first_image)
+            eng.super_resolve_u8_wait((i - 1) % 2, sr_host)
+        eng.super_resolve_u8_wait((steps - 1) % 2, sr_host)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    ms_e2e = timed_e2e(max(3, min(args.steps, 6)), 1)
     clk = clocks.stop() if clocks else None
     value = B * world / (ms_dev / 1e3)
     e2e = B * world / (ms_e2e / 1e3)
@@ -317,7 +337,8 @@ def run_ours(args, rank, world, local_rank):
                           "ms_per_unet_step": ms_dev / T, "noise": "on-device Philox (value), same (e2e)"},
                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(lr_host.nbytes),
                        "d2h_bytes_per_step": int(B * 3 * H * H * 4), "ms_per_step": ms_e2e,
-                       "api": "Engine.super_resolve_u8_host -> fdsr_super_resolve_u8 (uint8 LR host -> fp32 SR host)"},
+                       "api": "Engine.super_resolve_u8_submit / _wait -> fdsr_super_resolve_u8_submit / _wait (uint8 LR host -> "
+                              "fp32 SR host, two slots: one batch in flight ahead)"},
                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                "shard_invariant": shard_invariant,
                "psnr_mean_vs_synthetic_hr": (acc[1] / acc[2]).item() if acc[2].item() > 0 else None}

@@ -74,6 +74,9 @@ _SIGS = {
     "fdsr_trace_frames": (C.c_int32, [C.c_void_p]),
     "fdsr_super_resolve_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "fdsr_super_resolve_u8_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "fdsr_super_resolve_u8_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "fdsr_bicubic_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdsr_sse_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

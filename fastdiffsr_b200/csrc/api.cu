@@ -143,10 +143,19 @@ struct fdsr_ctx {
   unsigned long long* d_metric = nullptr;  // [B][4] integer accumulators of fdsr_metrics_u8
   size_t metric_bytes = 0;
   // pinned staging for the host-buffer path
-  uint8_t* h_pin = nullptr;
-  size_t h_pin_bytes = 0;
-  uint8_t* d_stage = nullptr;
-  size_t d_stage_bytes = 0;
+  // host-buffer path: two slots so that the copies of one batch overlap the sampling of the next
+  struct HostSlot {
+    uint8_t* h_pin = nullptr;      // pinned: [LR u8 | SR fp32 | status word]
+    size_t h_pin_bytes = 0;
+    uint8_t* d_stage = nullptr;    // device: [LR u8 | cond fp32 | SR fp32 | status word]
+    size_t d_stage_bytes = 0;
+    size_t in_b = 0, out_b = 0;
+    cudaEvent_t computed = nullptr, copied = nullptr;
+    bool busy = false;
+  };
+  static constexpr int kHostSlots = 2;
+  HostSlot slot[kHostSlots];
+  cudaStream_t copy_stream = nullptr;
   // graph cache
   bool use_graph = true;
   bool precise = false;  // FDSR_PRECISE_SWISH=1: fp32 Swish in the producers
@@ -1152,10 +1161,9 @@ int upload_layers(fdsr_ctx* c) {
     }
     // patch rings (see ConvCfg): N = 64 layers with 1x1-residual chunks use 2 full + 2 centre-box stages
     // (with three or more centre boxes per tile two 32 KB stages stall on the third: measured slower)
-    {
-      static const int max_center = [] { const char* e = getenv("FDSR_RINGS_MAXC"); return e ? atoi(e) : 2; }();
-      l.nR = (c->two_rings && any_center >= 1 && any_center <= max_center && l.N == 64) ? 2 : 0;
-    }
+    // (with three centre boxes per tile two 32 KB stages stall on the third: measured slower in both rounds,
+    //  ups.12.block2 189.6 -> 200.9 us as CTA pairs, profiles/r2/epilogue_costs.log)
+    l.nR = (c->two_rings && any_center >= 1 && any_center <= 2 && l.N == 64) ? 2 : 0;
     l.nG = l.nR ? 2 : (l.N >= 256 ? 2 : 3);
     for (int j = 0; j < l.nchunks; ++j) l.chunk[j].ring = (l.nR && l.chunk[j].center) ? 1 : 0;
     l.gn_C = k.gn_C;
@@ -1469,7 +1477,7 @@ int posterior_launch(fdsr_ctx* c, const float* x, const float* eps, const float*
 
 // The T-step loop on the context's buffers.  Everything that differs between two calls of the same shape (seed,
 // image offset, noise / trace pointers) is read from the SampleArgs slot in device memory.
-int sample_enqueue(fdsr_ctx* c, bool has_noise, bool has_trace, cudaStream_t st) {
+int sample_enqueue(fdsr_ctx* c, bool has_trace, cudaStream_t st) {
   const SampleArgs* args = reinterpret_cast<const SampleArgs*>(c->d_ws + c->off_seed);
   const int T = c->T, B = c->B;
   const int64_t per = int64_t(3) * c->H * c->W, numel = per * B;
@@ -1517,7 +1525,6 @@ int sample_enqueue(fdsr_ctx* c, bool has_noise, bool has_trace, cudaStream_t st)
   res2img_kernel<<<gb, 256, 0, st>>>(x, cond, sr, per, per, B, args, 0, sr3);
   ++c->launches;
   CUDA_TRY(c, cudaGetLastError());
-  (void)has_noise;
   return FDSR_OK;
 }
 
@@ -1664,8 +1671,13 @@ int fdsr_destroy(fdsr_ctx* c) {
   cudaFree(c->d_prof);
   cudaFree(c->d_bic_tmp);
   cudaFree(c->d_metric);
-  cudaFree(c->d_stage);
-  if (c->h_pin) cudaFreeHost(c->h_pin);
+  for (auto& sl : c->slot) {
+    cudaFree(sl.d_stage);
+    if (sl.h_pin) cudaFreeHost(sl.h_pin);
+    if (sl.computed) cudaEventDestroy(sl.computed);
+    if (sl.copied) cudaEventDestroy(sl.copied);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (auto& b : c->bic) {
     cudaFree(b.d_min);
     cudaFree(b.d_cnt);
@@ -1936,7 +1948,7 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
       CUDA_TRY(c, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
       const int64_t l0 = c->launches;
       CUDA_TRY(c, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      rc = sample_enqueue(c, noise != nullptr, trace != nullptr, cs);
+      rc = sample_enqueue(c, trace != nullptr, cs);
       cudaGraph_t g = nullptr;
       cudaError_t e = cudaStreamEndCapture(cs, &g);
       cudaStreamDestroy(cs);
@@ -1959,7 +1971,7 @@ int fdsr_sample(fdsr_ctx* c, const float* cond, const float* noise, uint64_t see
     CUDA_TRY(c, cudaGraphLaunch(hit->exec, st));
     c->launches += hit->launches;
   } else {
-    rc = sample_enqueue(c, noise != nullptr, trace != nullptr, st);
+    rc = sample_enqueue(c, trace != nullptr, st);
     if (rc) return rc;
   }
   CUDA_TRY(c, cudaMemcpyAsync(sr_out, c->d_ws + c->off_sr, bytes, cudaMemcpyDeviceToDevice, st));
@@ -1992,42 +2004,83 @@ int fdsr_bicubic_u8(fdsr_ctx* c, const uint8_t* lr, int32_t B, int32_t h, int32_
   return FDSR_OK;
 }
 
-int fdsr_super_resolve_u8(fdsr_ctx* c, const uint8_t* lr_host, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
-                          const float* noise_dev, uint64_t seed, float* sr_out_host, void* stream) {
-  if (!c || !lr_host || !sr_out_host) return fail(c, FDSR_E_INVALID, "null argument");
+int fdsr_super_resolve_u8_submit(fdsr_ctx* c, int32_t slot, const uint8_t* lr_host, int32_t B, int32_t h, int32_t w,
+                                 int32_t H, int32_t W, const float* noise_dev, uint64_t seed, void* stream) {
+  if (!c || !lr_host || slot < 0 || slot >= fdsr_ctx::kHostSlots) return fail(c, FDSR_E_INVALID, "bad argument");
   int rc = check_ready(c);
   if (rc) return rc;
+  fdsr_ctx::HostSlot& sl = c->slot[slot];
+  if (sl.busy) return fail(c, FDSR_E_STATE, "slot %d still holds a result: call fdsr_super_resolve_u8_wait first", slot);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t in_b = size_t(B) * h * w * 3, out_b = size_t(B) * 3 * H * W * 4;
-  const size_t need_pin = align_up(in_b, 256) + out_b;
-  if (need_pin > c->h_pin_bytes) {
-    if (c->h_pin) cudaFreeHost(c->h_pin);
-    c->h_pin = nullptr;
-    CUDA_TRY(c, cudaMallocHost(&c->h_pin, need_pin));
-    c->h_pin_bytes = need_pin;
+  if (!c->copy_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!sl.computed) {
+    CUDA_TRY(c, cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
   }
-  const size_t need_dev = align_up(in_b, 256) + 2 * out_b;
-  if (need_dev > c->d_stage_bytes) {
-    cudaFree(c->d_stage);
-    c->d_stage = nullptr;
-    CUDA_TRY(c, cudaMalloc(&c->d_stage, need_dev));
-    c->d_stage_bytes = need_dev;
+  const size_t in_b = size_t(B) * h * w * 3, out_b = size_t(B) * 3 * H * W * 4, in_a = align_up(in_b, 256);
+  const size_t need_pin = in_a + out_b + 256, need_dev = in_a + 2 * out_b + 256;
+  if (need_pin > sl.h_pin_bytes) {
+    if (sl.h_pin) cudaFreeHost(sl.h_pin);
+    sl.h_pin = nullptr;
+    sl.h_pin_bytes = 0;
+    CUDA_TRY(c, cudaMallocHost(&sl.h_pin, need_pin));
+    sl.h_pin_bytes = need_pin;
   }
-  uint8_t* d_lr = c->d_stage;
-  float* d_cond = reinterpret_cast<float*>(c->d_stage + align_up(in_b, 256));
-  float* d_sr = reinterpret_cast<float*>(c->d_stage + align_up(in_b, 256) + out_b);
-  float* h_sr = reinterpret_cast<float*>(c->h_pin + align_up(in_b, 256));
-  memcpy(c->h_pin, lr_host, in_b);
-  CUDA_TRY(c, cudaMemcpyAsync(d_lr, c->h_pin, in_b, cudaMemcpyHostToDevice, st));
+  if (need_dev > sl.d_stage_bytes) {
+    cudaFree(sl.d_stage);
+    sl.d_stage = nullptr;
+    sl.d_stage_bytes = 0;
+    CUDA_TRY(c, cudaMalloc(&sl.d_stage, need_dev));
+    sl.d_stage_bytes = need_dev;
+  }
+  sl.in_b = in_b;
+  sl.out_b = out_b;
+  uint8_t* d_lr = sl.d_stage;
+  float* d_cond = reinterpret_cast<float*>(sl.d_stage + in_a);
+  float* d_sr = reinterpret_cast<float*>(sl.d_stage + in_a + out_b);
+  uint8_t* d_flag = sl.d_stage + in_a + 2 * out_b;
+  memcpy(sl.h_pin, lr_host, in_b);
+  CUDA_TRY(c, cudaMemcpyAsync(d_lr, sl.h_pin, in_b, cudaMemcpyHostToDevice, st));
   rc = fdsr_bicubic_u8(c, d_lr, B, h, w, H, W, nullptr, d_cond, stream);
   if (rc) return rc;
   rc = fdsr_sample(c, d_cond, noise_dev, seed, d_sr, nullptr, B, H, W, stream);
   if (rc) return rc;
-  CUDA_TRY(c, cudaMemcpyAsync(h_sr, d_sr, out_b, cudaMemcpyDeviceToHost, st));
-  rc = fdsr_check_overflow(c, stream);  // (synchronises the stream)
-  if (rc) return rc;
-  memcpy(sr_out_host, h_sr, out_b);
+  // the batch's own copy of the status word (fp16 overflow flag), then clear it for the next batch
+  CUDA_TRY(c, cudaMemcpyAsync(d_flag, c->d_ws + kOffFlags, 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ws + kOffFlags, 0, 4, st));
+  CUDA_TRY(c, cudaEventRecord(sl.computed, st));
+  // device -> host on the copy stream: overlaps the next batch's sampling on `stream`
+  CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, sl.computed, 0));
+  CUDA_TRY(c, cudaMemcpyAsync(sl.h_pin + in_a, d_sr, out_b, cudaMemcpyDeviceToHost, c->copy_stream));
+  CUDA_TRY(c, cudaMemcpyAsync(sl.h_pin + in_a + out_b, d_flag, 4, cudaMemcpyDeviceToHost, c->copy_stream));
+  CUDA_TRY(c, cudaEventRecord(sl.copied, c->copy_stream));
+  sl.busy = true;
   return FDSR_OK;
+}
+
+int fdsr_super_resolve_u8_wait(fdsr_ctx* c, int32_t slot, float* sr_out_host) {
+  if (!c || !sr_out_host || slot < 0 || slot >= fdsr_ctx::kHostSlots) return fail(c, FDSR_E_INVALID, "bad argument");
+  fdsr_ctx::HostSlot& sl = c->slot[slot];
+  if (!sl.busy) return fail(c, FDSR_E_STATE, "slot %d has no batch in flight", slot);
+  CUDA_TRY(c, cudaEventSynchronize(sl.copied));
+  sl.busy = false;
+  const size_t in_a = align_up(sl.in_b, 256);
+  unsigned int flags = 0;
+  memcpy(&flags, sl.h_pin + in_a + sl.out_b, 4);
+  if (flags & 1u)
+    return fail(c, FDSR_E_OVERFLOW, "fp16 overflow: an activation exceeded +-65504 and was stored saturated; the result is "
+                                    "not trustworthy -- create the context with FDSR_DTYPE_BF16 for this network");
+  memcpy(sr_out_host, sl.h_pin + in_a, sl.out_b);
+  return FDSR_OK;
+}
+
+int fdsr_super_resolve_u8(fdsr_ctx* c, const uint8_t* lr_host, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                          const float* noise_dev, uint64_t seed, float* sr_out_host, void* stream) {
+  if (!c || !lr_host || !sr_out_host) return fail(c, FDSR_E_INVALID, "null argument");
+  if (c->slot[0].busy) return fail(c, FDSR_E_STATE, "slot 0 holds a pipelined batch: wait for it first");
+  int rc = fdsr_super_resolve_u8_submit(c, 0, lr_host, B, h, w, H, W, noise_dev, seed, stream);
+  if (rc) return rc;
+  return fdsr_super_resolve_u8_wait(c, 0, sr_out_host);
 }
 
 int fdsr_sse_u8(fdsr_ctx* c, const float* a, const float* b, int32_t B, int32_t H, int32_t W, double* sse,

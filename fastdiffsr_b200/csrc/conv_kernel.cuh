@@ -107,8 +107,7 @@ struct ConvCfg {
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + kABytes;
   static constexpr int kOffTable = kOffB + kBStages * kBStageBytes;
-  static constexpr int kOffGstat = kOffTable + kMaxGnC * 8;
-  static constexpr int kOffBias = kOffGstat + 64 * 8;
+  static constexpr int kOffBias = kOffTable + kMaxGnC * 8;
   static constexpr int kOffTstat = kOffBias + 256 * 4;
   static constexpr int kOffBar = kOffTstat + kEpiWarps * kRow * 4;  // one row of pair sums per epilogue warp
   // (+ the pair-mode relay barriers: the peer CTA's a_full / b_full / acc_empty as seen by the leader's MMA warp)

@@ -200,6 +200,27 @@ class Engine:
                                                        self._stream()), "fdsr_super_resolve_u8")
         return out
 
+    def super_resolve_u8_submit(self, slot: int, lr_host: np.ndarray, H: int, W: int, noise=None, seed: int = 0,
+                                image_offset: int = 0):
+        """Pipelined host path: enqueue one batch into `slot` (0 / 1) and return; see super_resolve_u8_wait."""
+        lr_host = np.ascontiguousarray(lr_host, dtype=np.uint8)
+        B, h, w, _ = lr_host.shape
+        self._check(self.lib.fdsr_set_image_offset(self._h, int(image_offset)), "fdsr_set_image_offset")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_super_resolve_u8_submit(self._h, slot, lr_host.ctypes.data_as(C.c_void_p), B, h, w, H, W,
+                                                              _ptr(noise), seed, self._stream()),
+                        "fdsr_super_resolve_u8_submit")
+        return (B, 3, H, W)
+
+    def super_resolve_u8_wait(self, slot: int, out: np.ndarray):
+        """Block until the batch in `slot` is on the host; fills the C-contiguous float32 array `out`."""
+        if out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise FdsrError("out must be a C-contiguous float32 array")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_super_resolve_u8_wait(self._h, slot, out.ctypes.data_as(C.c_void_p)),
+                        "fdsr_super_resolve_u8_wait")
+        return out
+
     def sse_u8(self, a, b):
         a, b = self._img(a, "a"), self._img(b, "b")
         B, _, H, W = a.shape

@@ -146,6 +146,14 @@ int fdsr_super_resolve_u8(fdsr_ctx* ctx, const uint8_t* lr_host, int32_t B, int3
                           int32_t H, int32_t W, const float* noise_dev, uint64_t seed,
                           float* sr_out_host, void* stream);
 
+/* The same, pipelined for throughput: two slots.  submit enqueues H2D, bicubic, sampling and — on an internal copy stream —
+ * the D2H of one batch into `slot` (0 or 1) and returns; wait blocks until that slot's result is in its pinned buffer,
+ * copies it to sr_out_host and reports FDSR_E_OVERFLOW if the fp16 guard fired for that batch.  With one batch submitted
+ * ahead, the copies and the host-side memcpy of batch i overlap the sampling of batch i+1. */
+int fdsr_super_resolve_u8_submit(fdsr_ctx* ctx, int32_t slot, const uint8_t* lr_host, int32_t B, int32_t h, int32_t w,
+                                 int32_t H, int32_t W, const float* noise_dev, uint64_t seed, void* stream);
+int fdsr_super_resolve_u8_wait(fdsr_ctx* ctx, int32_t slot, float* sr_out_host);
+
 /* New at the boundary (the reference precomputes it offline with PIL, data/prepare_data_mfe_dm.py
  * :30-40): bit-exact Pillow BICUBIC resize of uint8 HWC images (horizontal pass, uint8 rounding,
  * vertical pass; 22-bit fixed-point taps), then optional /255*2-1 to fp32 NCHW (data/util.py:66-75).

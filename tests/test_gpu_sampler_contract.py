@@ -264,3 +264,24 @@ def test_auto_dtype_falls_back_to_bf16(oracle, schedule):
     net16.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], "cuda")
     with pytest.raises(F.FdsrOverflowError):
         net16.super_resolution(cond, False, noise=nz)
+
+
+def test_pipelined_host_path_equals_synchronous(eng):
+    """fdsr_super_resolve_u8_submit / _wait (two slots, D2H on a copy stream) returns exactly what the synchronous call
+    returns, batch by batch, and refuses a slot that still holds a result."""
+    from fastdiffsr_b200 import FdsrError
+    rng = np.random.default_rng(11)
+    batches = [rng.integers(0, 256, size=(2, 16, 16, 3), dtype=np.uint8) for _ in range(4)]
+    want = [eng.super_resolve_u8_host(b, 64, 64, seed=40 + i, image_offset=2 * i).copy() for i, b in enumerate(batches)]
+    got = [np.empty((2, 3, 64, 64), dtype=np.float32) for _ in batches]
+    eng.super_resolve_u8_submit(0, batches[0], 64, 64, seed=40, image_offset=0)
+    with pytest.raises(FdsrError):
+        eng.super_resolve_u8_submit(0, batches[1], 64, 64, seed=41)
+    for i in range(1, 4):
+        eng.super_resolve_u8_submit(i % 2, batches[i], 64, 64, seed=40 + i, image_offset=2 * i)
+        eng.super_resolve_u8_wait((i - 1) % 2, got[i - 1])
+    eng.super_resolve_u8_wait(1, got[3])
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    with pytest.raises(FdsrError):
+        eng.super_resolve_u8_wait(0, got[0])

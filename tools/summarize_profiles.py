@@ -102,7 +102,8 @@ want = ["Duration", "SM Frequency", "Compute (SM) Throughput", "Memory Throughpu
         "Registers Per Thread", "Dynamic Shared Memory Per Block", "Issued Warp Per Scheduler", "Executed Instructions",
         "Warp Cycles Per Issued Instruction", "Achieved Active Warps Per SM"]
 names = {"1": "downs.1.block1 (64->64 3x3, N=64, 256^2)", "41": "ups.9.block2 (N=128, 128^2, GN + 1x1 residual chunks)",
-         "37": "ups.7 (up2x conv 256->256 as four 2x2 phase convs, N=256, 128^2)", "47": "ups.13.block1 (128->64, N=64, 256^2)"}
+         "37": "ups.7 (up2x conv 256->256 as four 2x2 phase convs, N=256, 128^2)", "47": "ups.13.block1 (128->64, N=64, 256^2)",
+         "16": "downs.10.block1 (256->256 3x3, N=256, 32^2)"}
 for f in sorted(glob.glob(os.path.join(rd, "conv*_details.csv"))):
     idx = os.path.basename(f).split("_")[0].replace("conv", "")
     rows = list(csv.reader(open(f)))
@@ -113,7 +114,7 @@ for f in sorted(glob.glob(os.path.join(rd, "conv*_details.csv"))):
         if r[iM] in want:
             lines.append(f"| {r[iM]} | {r[iV]} {r[iU]} |")
     raw = f.replace("_details", "_raw")
-    src = os.path.join("gpurun_out/profiles", os.path.basename(raw))
+    src = raw if os.path.exists(raw) else os.path.join("gpurun_out/profiles", os.path.basename(raw))
     if os.path.exists(src):
         rr = list(csv.reader(open(src)))
         d = dict(zip(rr[0], rr[2] if len(rr) > 2 else rr[1]))
