@@ -95,6 +95,7 @@ _SIGS = {
                                           C.c_void_p]),
     "fdsr_debug_role_cycles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int32,
                                          C.c_void_p]),
+    "fdsr_debug_timeline": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.c_void_p]),
     "fdsr_check_overflow": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fdsr_set_image_offset": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fdsr_debug_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64,

@@ -165,6 +165,8 @@ struct fdsr_ctx {
   bool pdl = true;       // FDSR_PDL=0: plain stream order between conv launches (no programmatic dependent launch)
   bool split_n = true;   // FDSR_SPLIT_N=0: never split a layer's output channels over two CTAs
   bool epi2 = true;        // FDSR_EPI2=0: producer-free layers keep one epilogue team (warps 4..11)
+  bool tail_help = true;   // FDSR_TAIL_HELP=0: the last tile of a CTA is drained by warps 4..11 alone
+  bool patch_first = true; // FDSR_PATCH_FIRST=0: weight stages are requested before griddepcontrol.wait, the first patch after
   bool half_tiles = true;  // FDSR_HALF_TILES=0: 32 x 8 tiles everywhere (the <= 64^2 wide layers then use split-N / single accumulators)
   bool stem_tma = true;  // FDSR_STEM_TMA=0: the 16-channel stem input is gathered by the producer warps
   bool fused_tail = true;  // FDSR_FUSED_TAIL=0: the sampler runs pack_input / final conv -> eps / posterior as separate kernels
@@ -1084,8 +1086,8 @@ int upload_layers(fdsr_ctx* c) {
   if (c->cfg.dtype == FDSR_DTYPE_FP32) return upload_layers_f32(c);
   const int B = c->B, H = c->H, W = c->W;
   if (!c->d_prof) {
-    CUDA_TRY(c, cudaMalloc(&c->d_prof, size_t(c->num_sms) * 32 * 8));
-    CUDA_TRY(c, cudaMemset(c->d_prof, 0, size_t(c->num_sms) * 32 * 8));
+    CUDA_TRY(c, cudaMalloc(&c->d_prof, size_t(c->num_sms) * kProfRoles * 64));
+    CUDA_TRY(c, cudaMemset(c->d_prof, 0, size_t(c->num_sms) * kProfRoles * 64));
   }
   std::vector<ConvLayer> L(c->convs.size());
   for (size_t i = 0; i < c->convs.size(); ++i) {
@@ -1227,6 +1229,8 @@ int upload_layers(fdsr_ctx* c) {
         for (int j = 0; j < l.nchunks; ++j) l.chunk[j].ring = 0;
       }
     }
+    l.tail2 = (c->tail_help && !l.epi2 && k.out_mode == kOutAct && l.N >= 64) ? 1 : 0;
+    l.patch_first = c->patch_first ? 1 : 0;
     l.prof = c->d_prof;
     l.flags = reinterpret_cast<unsigned int*>(c->d_ws + kOffFlags);
     {
@@ -1613,6 +1617,10 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->pair = !(e3 && e3[0] == '0');
     const char* e16 = getenv("FDSR_EPI2");
     c->epi2 = !(e16 && e16[0] == '0');
+    const char* e17 = getenv("FDSR_TAIL_HELP");
+    c->tail_help = !(e17 && e17[0] == '0');
+    const char* e18 = getenv("FDSR_PATCH_FIRST");
+    c->patch_first = !(e18 && e18[0] == '0');
     const char* e15 = getenv("FDSR_HALF_TILES");
     c->half_tiles = !(e15 && e15[0] == '0');
     const char* e13 = getenv("FDSR_STEM_TMA");
@@ -2220,7 +2228,7 @@ int fdsr_debug_role_cycles(fdsr_ctx* c, int32_t op, int32_t t, int64_t* out_host
   if (!c->d_ws) return fail(c, FDSR_E_STATE, "run a forward first");
   if (op < 0 || op >= int(c->ops.size()) || c->ops[op].kind != 0) return fail(c, FDSR_E_INVALID, "op is not a conv");
   if (c->cfg.dtype == FDSR_DTYPE_FP32) return fail(c, FDSR_E_INVALID, "role cycles exist for the tensor-core kernel only");
-  const int n = c->num_sms * 32;
+  const int n = c->num_sms * kProfRoles * 8;
   if (cap < n) return fail(c, FDSR_E_INVALID, "capacity too small");
   if (c->layers_dirty) {
     rc = upload_layers(c);
@@ -2234,6 +2242,40 @@ int fdsr_debug_role_cycles(fdsr_ctx* c, int32_t op, int32_t t, int64_t* out_host
   CUDA_TRY(c, cudaMemcpyAsync(out_host, c->d_prof, size_t(n) * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(c, cudaStreamSynchronize(st));
   return n;
+}
+
+// In-situ timeline (FDSR_PROFILE builds): `reps` complete UNet evaluations back to back on `stream`, launched exactly as
+// the sampler launches them (programmatic dependent launch, no graph), every conv op writing its CTA stamps into its
+// own slice; out_host receives [op][num_sms][kProfRoles][8] of the LAST evaluation (ops that are not convs stay zero).
+int fdsr_debug_timeline(fdsr_ctx* c, int32_t t, int32_t reps, int64_t* out_host, int64_t cap, void* stream) {
+  if (!c || !out_host) return fail(c, FDSR_E_INVALID, "null argument");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!c->d_ws) return fail(c, FDSR_E_STATE, "run a forward first");
+  if (c->cfg.dtype == FDSR_DTYPE_FP32) return fail(c, FDSR_E_INVALID, "timelines exist for the tensor-core kernel only");
+  const size_t per_op = size_t(c->num_sms) * kProfRoles * 8, n = per_op * c->ops.size();
+  if (size_t(cap) < n) return fail(c, FDSR_E_INVALID, "capacity too small");
+  if (c->layers_dirty) {
+    rc = upload_layers(c);
+    if (rc) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long* buf = nullptr;
+  CUDA_TRY(c, cudaMalloc(&buf, n * 8));
+  for (size_t i = 0; i < c->ops.size(); ++i)
+    if (c->ops[i].kind == 0) c->h_layers[c->ops[i].idx].prof = buf + i * per_op;
+  for (int r = 0; r < reps && rc == FDSR_OK; ++r) {
+    if (r + 1 == reps) cudaMemsetAsync(buf, 0, n * 8, st);
+    rc = unet_dispatch(c, t, st, false);
+  }
+  cudaError_t e = cudaMemcpyAsync(out_host, buf, n * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  for (size_t i = 0; i < c->ops.size(); ++i)
+    if (c->ops[i].kind == 0) c->h_layers[c->ops[i].idx].prof = c->d_prof;
+  cudaFree(buf);
+  if (rc) return rc;
+  CUDA_TRY(c, e);
+  return int(c->ops.size());
 }
 
 int fdsr_check_overflow(fdsr_ctx* c, void* stream) {

@@ -142,6 +142,9 @@ struct ConvLayer {
                            // grid, every tap position is shifted by (py*kPatchW + px), weights are per phase
   int32_t epi2;            // 1: layers without producer work (every chunk raw, patches by TMA: up / down-sampling convs,
                            //    stem) turn producer warps 12..19 into a second epilogue team (odd 32-column blocks)
+  int32_t tail2;           // 1: producer warps 12..19 join the epilogue of the CTA's LAST tile as a second team (layers with
+                           //    producer work; the last tile's epilogue is exposed — nothing is left to overlap it with)
+  int32_t patch_first;     // 1: the loader requests the CTA's first input patch before its first weight stages
   int32_t tile_h;          // output rows per CTA tile: 32 (two 128-row MMA tiles) or 16 (one: "half tiles", see upload_layers)
   int32_t tiles_x, tiles_y, ntiles;
   int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)

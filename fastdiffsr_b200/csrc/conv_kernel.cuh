@@ -245,6 +245,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {  // (the waiters call named_bar_sync)
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -289,6 +292,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane)
 }
 
 // Optional role-level cycle accounting (tools/ only; compiled in with -DFDSR_PROFILE).
+constexpr int kProfRoles = 5;  // 8 slots each per CTA: MMA, epilogue, producers, timeline, anchor
 #ifdef FDSR_PROFILE
 #define PROF_DECL long long pt_ = clock64(), pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define PROF_MARK(slot)              \
@@ -300,13 +304,30 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane)
 #define PROF_FLUSH(role)                                                                  \
   do {                                                                                    \
     if (L.prof != nullptr)                                                                \
-      for (int k_ = 0; k_ < 8; ++k_) L.prof[(size_t(blockIdx.x) * 4 + (role)) * 8 + k_] = pacc_[k_]; \
+      for (int k_ = 0; k_ < 8; ++k_) L.prof[(size_t(blockIdx.x) * kProfRoles + (role)) * 8 + k_] = pacc_[k_]; \
   } while (0)
-// timeline of one CTA (role 3): cycles since kernel entry at which an event FIRST happened (slot written once)
-#define PROF_T0 const long long pt0_ = clock64()
+// timeline of one CTA (role 3): cycles since kernel entry at which an event FIRST happened (slot written once);
+// role 4 anchors it: {SM id, the SM's clock64 at kernel entry, %globaltimer at entry} — consecutive launches on the
+// same SM share the clock, which gives the idle time of the tensor pipe between two layers inside a running sampler
+#define PROF_T0                                                                 \
+  const long long pt0_ = clock64();                                             \
+  if (threadIdx.x == 0 && L.prof != nullptr) {                                  \
+    unsigned sm_;                                                               \
+    long long gt_;                                                              \
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));                            \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                     \
+    long long* p_ = L.prof + (size_t(blockIdx.x) * kProfRoles + 4) * 8;         \
+    p_[0] = sm_;                                                                \
+    p_[1] = pt0_;                                                               \
+    p_[2] = gt_;                                                                \
+  }
 #define PROF_TS(slot)                                                                      \
   do {                                                                                     \
-    if (L.prof != nullptr) L.prof[(size_t(blockIdx.x) * 4 + 3) * 8 + (slot)] = clock64() - pt0_; \
+    if (L.prof != nullptr) L.prof[(size_t(blockIdx.x) * kProfRoles + 3) * 8 + (slot)] = clock64() - pt0_; \
+  } while (0)
+#define PROF_TS4(slot) /* anchor-row extras: 3 = accumulator of the CTA's last tile complete (tensor pipe drained) */ \
+  do {                                                                                     \
+    if (L.prof != nullptr) L.prof[(size_t(blockIdx.x) * kProfRoles + 4) * 8 + (slot)] = clock64() - pt0_; \
   } while (0)
 #else
 #define PROF_DECL
@@ -314,6 +335,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane)
 #define PROF_FLUSH(role)
 #define PROF_T0
 #define PROF_TS(slot)
+#define PROF_TS4(slot)
 #endif
 
 // kFast: GroupNorm-affine + Swish in packed fp16 (tanh form); otherwise fp32 EX2/RCP.
@@ -404,6 +426,8 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   // (the loader and the producer warps first fetch constants — weights, GroupNorm gamma / beta — and wait in their roles)
   const bool epi_team2 = L.epi2 != 0 && warp >= 4 + kEpiWarps;  // (layers without producer work)
   const bool is_producer = (warp == 2 || warp == 3 || warp >= 4 + kEpiWarps) && !epi_team2;
+  bool epi_role = (warp >= 4 && warp < 4 + kEpiWarps) || epi_team2;
+  bool tail_helper = false;  // producer warps 12..19 after their own work: second epilogue team for the CTA's last tile
   if (warp != 1 && !is_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid == 0) PROF_TS(1);  // previous launch complete
 
@@ -590,6 +614,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     // Patches are the previous layer's output: no patch request before griddepcontrol.wait.  Weights are
     // constants, so the first weight stages are requested before it and land while the previous launch drains.
     bool dep_ok = !tma_in;
+    // ... unless the layer asks for its first patch FIRST (L.patch_first, the default): a CTA only becomes resident when
+    // the previous launch's CTA on this SM has exited, so the dependency resolves within a few microseconds anyway, and
+    // then 64 - 96 KB of weight stages queued ahead of the 43 KB patch on the SM's inbound link delay the longer chain
+    // (patch -> GroupNorm pass -> first MMA; the weights are only needed at the end of it).  Measured -0.6 % of a UNet
+    // step's op time, -1.6 % of the sampler at B = 16 (profiles/r2/ab_tail.log).
+    if (L.patch_first != 0 && !dep_ok) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      dep_ok = true;
+    }
     const int total = (tile_end - tile_begin) * L.nchunks;
     // patch cursor
     int a_next = tma_in ? 0 : total, a_c = 0, a_gs = 0, a_gph = 0, a_rs = 0, a_rph = 0;
@@ -720,24 +753,294 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       }
       if (!progress) __nanosleep(32);
     }
-  } else if ((warp >= 4 && warp < 4 + kEpiWarps) || epi_team2) {
+  } else if (!epi_role) {
+    // =========================================================== input producers
+    const int pw = warp < 4 ? warp - 2 : warp - 10;  // warps 2,3,12..19 -> 0..9
+    const int pidx = pw * 32 + lane;                  // 0..319
+    const int H = L.H, W = L.W, mode = L.mode, tiles_x = L.tiles_x;
+    __half* table_h = reinterpret_cast<__half*>(table);
+    int as = 0, aph = 0, cur_b = -1;
+    int b = tile_first / tiles_per_img;
+    int rem = tile_first - b * tiles_per_img;
+    int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    PROF_DECL;
+
+    // GroupNorm scale/shift table of sample `bb` (virtual concat of the GroupNorm sources).
+    // Everything that does not depend on the previous launch — gamma / beta of this thread's two channels, the pair
+    // range of their groups, the reciprocals — is fetched BEFORE griddepcontrol.wait; afterwards a table costs one
+    // round of independent statistics loads (every thread sums the <= 8 channel pairs of its own group straight from
+    // L2: no staging, no cross-thread hand-off), three fp64 operations, an rsqrt and one barrier.  This sits on the
+    // critical path of every launch (statistics -> table -> first normalised patch -> first MMA).
+    const int cpg = L.gn_C > 0 ? L.gn_C / L.gn_groups : 2, ppg = cpg >> 1, p0 = L.src[0].C >> 1;
+    float ga[2] = {0.f, 0.f}, be[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = pidx + j * kProdThreads;
+      if (c < L.gn_C) {
+        ga[j] = L.gamma[c];
+        be[j] = L.beta[c];
+      }
+    }
+    const double inv_sum = L.gn_inv_sum, inv_sq = L.gn_inv_sq;  // 1 / (fixed-point scale * elements per group), host-side
+    bool table_valid = false;
+    auto build_table = [&](int bb) {
+      if (table_valid) named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
+      table_valid = true;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = pidx + j * kProdThreads;
+        if (c < L.gn_C) {
+          const int pv0 = (c / cpg) * ppg;
+          long long Si = 0, Qi = 0;
+#pragma unroll 8
+          for (int k = 0; k < ppg; ++k) {
+            const int pv = pv0 + k;
+            const int si = pv < p0 ? 0 : 1;
+            const int pl = pv < p0 ? pv : pv - p0;
+            const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(
+                reinterpret_cast<const long long*>(L.src[si].stats) + (size_t(bb) * (L.src[si].C >> 1) + pl) * 2));
+            Si += st.x;
+            Qi += st.y;
+          }
+          const double mean = double(Si) * inv_sum;
+          double var = double(Qi) * inv_sq - mean * mean;
+          var = var > 0.0 ? var : 0.0;
+          const float rstd = rsqrtf(float(var) + L.gn_eps);
+          const float sc = ga[j] * rstd;
+          const float sh = be[j] - float(mean) * sc;
+          if constexpr (kFast && Cvt<T>::kFmt == 0) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
+            table_h[c] = __float2half_rn(0.5f * sc);
+            table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
+          } else if constexpr (kFast) {  // bf16 storage: fp32 affine, then the packed-half tanh form
+            table[c] = make_float2(0.5f * sc, 0.5f * sh);
+          } else {
+            table[c] = make_float2(sc, sh);
+          }
+        }
+      }
+      named_bar_sync(1, kProdThreads);
+    };
+    // (a dry run of build_table on stale statistics before the wait, to warm its code path, measured 0.4 % slower)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (L.a_tma != 0) {
+      // ----------------------------------------------------------------- TMA-fed layers: the loader warp's
+      // tensor loads land the raw 128B-swizzled patch in the stage (out-of-image positions zero);
+      // these warps apply GroupNorm + Swish in place and hand the stage to the MMA warp.  The thread
+      // owns 16-byte slot (pidx & 7) of positions (pidx >> 3) + 40 i: byte pidx*16 + i*5120 of the stage
+      // (conflict-free: a warp covers 512 contiguous bytes).  40 positions are 5 swizzle periods, so the
+      // slot's logical channel group depends only on the stage
+      // (stage s starts 341 s = 5 s mod 8 rows into the swizzle period)
+      const int pos0 = pidx >> 3;
+      const int py0 = pos0 / kPatchW, px0 = pos0 - py0 * kPatchW;  // position of unit i: (py0 + 4 i, px0)
+      uint32_t smask = 0u;  // unit i = position pos0 + 40 i exists in the (TH + 2) x 10 patch
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i) smask |= (pos0 + 40 * i < npos) ? (1u << i) : 0u;
+      uint32_t rph = 0u;  // bit s: parity of the next phase of raw_full(s) (only GroupNorm chunks use it)
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        if (L.gn_C > 0 && b != cur_b) {
+          cur_b = b;
+          build_table(b);
+          if (pidx == 0 && tile == tile_begin) PROF_TS(2);  // GroupNorm table of the first image built
+        }
+        // units inside the image (padding must stay zero: swish(GN(0)) != 0)
+        const int y0 = ty * TH - 1 + py0, x0 = tx * kTileW - 1 + px0;
+        uint32_t vmask = 0u;
+        if (unsigned(x0) < unsigned(W)) {
+#pragma unroll
+          for (int i = 0; i < kMaxUnits; ++i) vmask |= unsigned(y0 + 4 * i) < unsigned(H) ? (1u << i) : 0u;
+          vmask &= smask;
+        }
+        PROF_MARK(0);
+        for (int c = 0; c < L.nchunks; ++c) {
+          const ConvChunk& ck = L.chunk[c];
+          if (ck.gn == 0) {  // raw chunk: the tensor load completes a_full by itself
+            if (ck.ring == 0 && ++as == nG) as = 0;
+            continue;
+          }
+          mbar_wait(bar_raw_full(as), (rph >> as) & 1u);
+          rph ^= 1u << as;
+          if (pidx == 0 && tile == tile_begin && c == 0) PROF_TS(3);  // first patch landed
+          PROF_MARK(1);
+          if (!(L.dbg & 2)) {
+            const int cgs = (pidx & 7) ^ ((pos0 + 5 * as) & 7);
+            float sc[8], sh[8];
+            uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
+            if constexpr (kFast && Cvt<T>::kFmt == 0) {
+              hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cgs * 8);
+              hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cgs * 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 e = table[ck.vc0 + cgs * 8 + j];
+                sc[j] = e.x;
+                sh[j] = e.y;
+              }
+            }
+            const uint32_t a0 = sA + as * kAStageBytes + uint32_t(pidx) * 16;  // (GroupNorm chunks: ring 0)
+            uint4 rv[kMaxUnits];
+#pragma unroll
+            for (int i = 0; i < kMaxUnits; ++i)
+              if ((vmask >> i) & 1u) rv[i] = lds128(a0 + i * (40 * 128));
+            if (ck.gn == 1) {
+#pragma unroll
+              for (int i = 0; i < kMaxUnits; ++i)
+                if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_swish_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
+            } else {  // GroupNorm without activation
+#pragma unroll
+              for (int i = 0; i < kMaxUnits; ++i)
+                if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_affine_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
+            }
+            fence_proxy_async_smem();
+          }
+          PROF_MARK(3);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_full(as));
+          if (++as == nG) as = 0;
+        }
+        if ((tx += kTStep) >= tiles_x) {
+          tx -= tiles_x;
+          if (++ty == L.tiles_y) { ty = 0; ++b; }
+        }
+      }
+    } else {
+      // ----------------------------------------------------------------- gathered layers (nearest-upsample,
+      // space-to-depth, the 16-channel stem): predicated 16-byte global loads into registers,
+      // GroupNorm + Swish, 16-byte stores into the no-swizzle [channel group][position][8 ch] patch
+      const int lg = ncg == 8 ? 3 : (ncg == 4 ? 2 : (ncg == 2 ? 1 : 0));
+      const int cg = pidx & (ncg - 1);
+      const int nunits = kPatchPos * ncg;
+      // per-thread patch coordinates of the (up to) 9 16-byte units it fills: fixed for the launch
+      uint32_t pcoord[kMaxUnits];  // py | px << 8
+      uint32_t emask = 0u, smask = 0u;  // bit i: unit i carries data / unit i has a smem slot to fill
+      uint32_t cenmask = 0u;            // bit i: unit i lies in the 32x8 centre of the patch (no halo)
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i) {
+        const int u = pidx + i * kProdThreads;
+        const int pos = u >> lg;
+        const int py = pos / kPatchW, px = pos - py * kPatchW;
+        bool ex = u < nunits;
+        smask |= ex ? (1u << i) : 0u;
+        if (mode == kModeS2D && (py > kTileH || px > kTileW)) ex = false;  // 33x9 block patch
+        emask |= ex ? (1u << i) : 0u;
+        cenmask |= (py >= 1 && py <= kTileH && px >= 1 && px <= kTileW) ? (1u << i) : 0u;
+        pcoord[i] = uint32_t(py) | (uint32_t(px) << 8);
+      }
+      const int shl = mode == kModeS2D ? 1 : 0, shr = mode == kModeUp2x ? 1 : 0;
+      const int src_w = mode == kModeS2D ? 2 * W : (mode == kModeUp2x ? (W >> 1) : W);
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
+        if (L.gn_C > 0 && b != cur_b) {
+          cur_b = b;
+          build_table(b);
+        }
+        // ---- source pixel offsets of this thread's patch positions; vmask bit i = inside the image
+        int pixoff[kMaxUnits];
+        uint32_t vmask = 0u;
+#pragma unroll
+        for (int i = 0; i < kMaxUnits; ++i) {
+          const int y = y0 + int(pcoord[i] & 0xffu), x = x0 + int((pcoord[i] >> 8) & 0xffu);
+          const bool ok = ((emask >> i) & 1u) != 0u && unsigned(y) < unsigned(H) && unsigned(x) < unsigned(W);
+          const int off = ((y << shl) >> shr) * src_w + ((x << shl) >> shr);
+          pixoff[i] = ok ? off : 0;
+          vmask |= ok ? (1u << i) : 0u;
+        }
+        PROF_MARK(0);
+        for (int c = 0; c < L.nchunks; ++c) {
+          if (L.dbg & 2) {  // experiment: producers only hand over (stale) stages
+            mbar_wait(bar_a_empty(as), aph ^ 1);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_full(as));
+            if (++as == kAStages) { as = 0; aph ^= 1; }
+            continue;
+          }
+          const ConvChunk& ck = L.chunk[c];
+          const ConvSrc& s = L.src[ck.src];
+          const int sC = s.C;
+          const uint32_t tmask = ck.gn != 0 ? vmask : 0u;  // units that get GroupNorm + Swish
+          // a chunk whose only tap is the centre one (one space-to-depth plane) never reads the halo:
+          // neither load nor store it
+          const uint32_t cm = (ck.ntaps == 1 && ck.tap_pos[0] == kPatchW + 1) ? cenmask : 0xffffffffu;
+          const uint32_t lmask = vmask & cm, stmask = smask & cm;
+          const bool gn = ck.gn != 0;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(
+              reinterpret_cast<const T*>(s.ptr) + (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8);
+          const uint32_t pix_bytes = uint32_t(sC) * 2u;
+          uint4 rv[kMaxUnits];
+#pragma unroll
+          for (int i = 0; i < kMaxUnits; ++i)
+            rv[i] = ldg16_pred(base + uint32_t(pixoff[i]) * pix_bytes, ((lmask >> i) & 1u) != 0u);
+          float sc[8], sh[8];
+          uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
+          if (gn) {
+            if constexpr (kFast && Cvt<T>::kFmt == 0) {
+              hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cg * 8);
+              hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cg * 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 e = table[ck.vc0 + cg * 8 + j];
+                sc[j] = e.x;
+                sh[j] = e.y;
+              }
+            }
+          }
+          PROF_MARK(1);
+          mbar_wait(bar_a_empty(as), aph ^ 1);
+          PROF_MARK(2);
+          const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes + uint32_t(pidx >> lg) * 16;
+#pragma unroll
+          for (int i = 0; i < kMaxUnits; ++i) {
+            if ((stmask >> i) & 1u) {
+              uint4 o = rv[i];
+              if ((tmask >> i) & 1u)
+                o = ck.gn == 1 ? gn_swish_unit<T, kFast>(o, hsc, hsh, sc, sh) : gn_affine_unit<T, kFast>(o, hsc, hsh, sc, sh);
+              sts128(dst0 + uint32_t((i * kProdThreads) >> lg) * 16, o);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_full(as));
+          PROF_MARK(3);
+          if (++as == kAStages) { as = 0; aph ^= 1; }
+        }
+        if ((tx += kTStep) >= tiles_x) {
+          tx -= tiles_x;
+          if (++ty == L.tiles_y) { ty = 0; ++b; }
+        }
+      }
+    }
+    if (pidx == 0) PROF_FLUSH(2);
+    // Tail help (L.tail2): the epilogue of a CTA's LAST tile has no MMAs left to hide behind — the tensor pipe of the SM
+    // idles until the launch ends (3 - 9 us per layer, tools/timeline.py).  Producer warps 12..19 have finished by then
+    // and share warps 4..11's TMEM lane quarters: they join as a second team for that one tile.
+    if (L.tail2 != 0 && warp >= 4 + kEpiWarps && tile_end > tile_begin) {
+      tail_helper = true;
+      epi_role = true;
+    }
+  }
+  if (epi_role) {
     // =========================================================== epilogue
     // Team 0 = warps 4..11.  Layers whose producer warps have nothing to do (L.epi2: every chunk raw and TMA-fed — these
     // layers are short on MMAs per tile and bound by this role) add warps 12..19 as team 1: the same (lane quarter, MMA
     // tile) assignment, the odd 32-column blocks, their own staging blocks, the same statistics rows.
-    const int team = epi_team2 ? 1 : 0;
-    const int nteams = L.epi2 ? 2 : 1, nepi = nteams * kEpiThreads;
+    // The last tile of layers WITH producer work (L.tail2): warps 12..19 arrive here when their patches are done
+    // (tail_helper) and take the team-1 share of that tile only.
+    const int team = (epi_team2 || tail_helper) ? 1 : 0;
+    const int nteams0 = L.epi2 ? 2 : 1, nepi0 = nteams0 * kEpiThreads;  // teams / threads on every tile
+    const bool tail2 = L.tail2 != 0;
     const int ew = team ? warp - (4 + kEpiWarps) : warp - 4;   // 0..7
     const int q = ew & 3;              // TMEM lane quarter owned by this warp (== warp % 4)
     // full tiles: one warpgroup per 128-row MMA tile; half tiles: both warpgroups drain the one MMA tile, warpgroup h
     // taking the 32-column blocks with (cb & 1) == h (a warp may only touch the TMEM lane quarter warp % 4)
     const int mt = two_mt ? ew >> 2 : 0;
-    const int cb_first = two_mt ? team : (ew >> 2), cb_step = two_mt ? nteams : 2;
     const int et = team ? kEpiThreads + (tid - 32 * (4 + kEpiWarps)) : tid - 128;          // 0..255 (team 0), 256..511
-    const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride + n_off;
-    for (int i = et; i < kRow; i += nepi) bias_s[i] = i < N ? bias_g[i] : 0.f;
-    for (int i = et; i < kEpiWarps * kRow; i += nepi) tstat[i] = 0.f;
-    named_bar_sync(2, nepi);
+    if (!tail_helper) {
+      const float* bias_g = L.bias + size_t(t_step) * L.bias_tstride + n_off;
+      for (int i = et; i < kRow; i += nepi0) bias_s[i] = i < N ? bias_g[i] : 0.f;
+      for (int i = et; i < kEpiWarps * kRow; i += nepi0) tstat[i] = 0.f;
+      named_bar_sync(2, nepi0);
+    }
     const int su = L.out_su;  // channel pairs per statistics entry (1, 2, 4 or 8)
     const int m = q * 32 + lane, g = m >> 3, r = m & 7;
     const bool act = L.out_mode == kOutAct;
@@ -758,23 +1061,45 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     const int H = L.H, W = L.W, tiles_x = L.tiles_x;
     const uint32_t lane_base = tmem + (uint32_t(q * 32) << 16);
     const uint32_t run_addr = lane_base + Cfg::kStatCol0 + mt * N;  // running sums (kStatsInTmem)
-    if (Cfg::kStatsInTmem && do_stats) {
+    if (Cfg::kStatsInTmem && do_stats && !tail_helper) {
       uint32_t z[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) z[j] = 0u;
-      for (int cb = cb_first; cb < Cfg::kNcb; cb += cb_step) tmem_st32(run_addr + cb * 32, z);
+      for (int cb = team; cb < Cfg::kNcb; cb += nteams0) tmem_st32(run_addr + cb * 32, z);  // (N = 64: full tiles only)
       tmem_st_wait();
     }
-    int acc = 0, accph = 0;
-    int b = tile_first / tiles_per_img;
-    int rem = tile_first - b * tiles_per_img;
+    // a helper starts at the CTA's last tile: its accumulator stage / parity and its position follow from the tile count
+    const int epi_begin = tail_helper ? tile_end - 1 : tile_begin;
+    int acc = (epi_begin - tile_begin) % nacc, accph = ((epi_begin - tile_begin) / nacc) & 1;
+    const int epi_first = tile_first + (epi_begin - tile_begin) * kTStep;
+    int b = epi_first / tiles_per_img;
+    int rem = epi_first - b * tiles_per_img;
     int ty = rem / tiles_x, tx = rem - ty * tiles_x;
     // fp16 storage: values beyond +-65504 are stored saturated AND reported through the context's overflow flag, so that
     // the host can fail loudly / re-run in the bf16 mode instead of returning a silently clipped image
     constexpr bool kOverflowCheck = Cvt<T>::kFmt == 0;
     float vmax = 0.f;
     PROF_DECL;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = epi_begin; tile < tile_end; ++tile) {
+      // teams on this tile, and the 32-column blocks of this warp: full tiles — one warpgroup per 128-row MMA tile, team t
+      // takes blocks t, t + nteams, ...; half tiles — both warpgroups (h = ew >> 2) of a team drain the one MMA tile,
+      // blocks h + 2 t, + 2 nteams, ...
+      const bool helped = tail2 && tile + 1 == tile_end;
+      const int nteams = (L.epi2 != 0 || helped) ? 2 : 1, nepi = nteams * kEpiThreads;
+      const int cb_first = two_mt ? team : (ew >> 2) + 2 * team, cb_step = two_mt ? nteams : 2 * nteams;
+      const int stat_bar = helped ? 3 : 2;  // (the helpers may already wait on theirs while team 0 still uses barrier 2)
+      if (helped) {
+        // Hand-over: everything team 0 did on earlier tiles — bias / statistics rows initialised, the previous tile's
+        // statistics flushed, its running TMEM sums stored — happens before the helpers touch the same rows and columns
+        if (tail_helper) {
+          named_bar_sync(4, 2 * kEpiThreads);
+          tc_fence_after();
+        } else {
+          tc_fence_before();
+          __threadfence_block();
+          named_bar_arrive(4, 2 * kEpiThreads);
+        }
+      }
       const int x = tx * kTileW + r, y = ty * TH + mt * 16 + g;
       const bool valid = y < H && x < W;
       const bool all_valid = __all_sync(0xffffffffu, valid);
@@ -807,6 +1132,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       }
       mbar_wait(bar_acc_full(acc), accph);
       PROF_MARK(0);
+      if (et == 0 && tile + 1 == tile_end) PROF_TS4(3);
       tc_fence_after();
       const uint32_t taddr = lane_base + acc * acc_cols + mt * Cfg::kAccStride;
 #pragma unroll 1
@@ -1008,7 +1334,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       if (Cfg::kStatsInTmem && do_stats) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+      if (lane == 0 && !tail_helper) mbar_arrive(bar_acc_empty(acc));  // (nobody waits for the last tile's)
       PROF_MARK(1);
       if (++acc == nacc) { acc = 0; accph ^= 1; }
       // next tile coordinates (no divisions in the loop)
@@ -1039,7 +1365,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           }
           // warps in fixed order, then order-independent 64-bit fixed-point atomics: the statistics
           // (and therefore every activation) are bitwise reproducible run to run
-          named_bar_sync(2, nepi);
+          named_bar_sync(stat_bar, nepi);
           // every warp total is converted to fixed point BEFORE the warps are added: integer addition is associative, so
           // the CTA's contribution does not depend on how the same 32-pixel warp blocks are grouped into tiles (full / half
           // tiles, split-N) — the tile shape may follow the batch size without changing a single bit of the result
@@ -1050,273 +1376,18 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             for (int w8 = 0; w8 < kEpiWarps; ++w8) tsum += __float2ll_rn(tstat[w8 * kRow + i] * sc);
             atomicAdd(L.out_stats + size_t(b_cur) * n_full + n_off + i, static_cast<unsigned long long>(tsum));
           }
-          named_bar_sync(2, nepi);
+          if (tile + 1 < tile_end) named_bar_sync(stat_bar, nepi);  // (the rows are rewritten by the next tile)
         }
       }
       PROF_MARK(2);
     }
     if (kOverflowCheck && vmax > 65504.f && L.flags != nullptr) atomicOr(L.flags, 1u);
-    if (lane == 0) bulk_wait_all0();  // outstanding bulk tensor stores of this warp
+    // outstanding bulk tensor stores of this warp (waiting only for their shared-memory READS — the writes are flushed
+    // at grid end anyway — measured no faster: profiles/r2/ab_tail.log)
+    if (lane == 0) bulk_wait_all0();
     if (et == 0) PROF_TS(6);  // epilogue of the last tile done, stores complete
     if (et == 0) PROF_FLUSH(1);
     (void)et;
-  } else {
-    // =========================================================== input producers
-    const int pw = warp < 4 ? warp - 2 : warp - 10;  // warps 2,3,12..19 -> 0..9
-    const int pidx = pw * 32 + lane;                  // 0..319
-    const int H = L.H, W = L.W, mode = L.mode, tiles_x = L.tiles_x;
-    __half* table_h = reinterpret_cast<__half*>(table);
-    int as = 0, aph = 0, cur_b = -1;
-    int b = tile_first / tiles_per_img;
-    int rem = tile_first - b * tiles_per_img;
-    int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    PROF_DECL;
-
-    // GroupNorm scale/shift table of sample `bb` (virtual concat of the GroupNorm sources).
-    // Everything that does not depend on the previous launch — gamma / beta of this thread's two channels, the pair
-    // range of their groups, the reciprocals — is fetched BEFORE griddepcontrol.wait; afterwards a table costs one
-    // round of independent statistics loads (every thread sums the <= 8 channel pairs of its own group straight from
-    // L2: no staging, no cross-thread hand-off), three fp64 operations, an rsqrt and one barrier.  This sits on the
-    // critical path of every launch (statistics -> table -> first normalised patch -> first MMA).
-    const int cpg = L.gn_C > 0 ? L.gn_C / L.gn_groups : 2, ppg = cpg >> 1, p0 = L.src[0].C >> 1;
-    float ga[2] = {0.f, 0.f}, be[2] = {0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = pidx + j * kProdThreads;
-      if (c < L.gn_C) {
-        ga[j] = L.gamma[c];
-        be[j] = L.beta[c];
-      }
-    }
-    const double inv_sum = L.gn_inv_sum, inv_sq = L.gn_inv_sq;  // 1 / (fixed-point scale * elements per group), host-side
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    bool table_valid = false;
-    auto build_table = [&](int bb) {
-      if (table_valid) named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
-      table_valid = true;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = pidx + j * kProdThreads;
-        if (c < L.gn_C) {
-          const int pv0 = (c / cpg) * ppg;
-          long long Si = 0, Qi = 0;
-#pragma unroll 8
-          for (int k = 0; k < ppg; ++k) {
-            const int pv = pv0 + k;
-            const int si = pv < p0 ? 0 : 1;
-            const int pl = pv < p0 ? pv : pv - p0;
-            const longlong2 st = __ldg(reinterpret_cast<const longlong2*>(
-                reinterpret_cast<const long long*>(L.src[si].stats) + (size_t(bb) * (L.src[si].C >> 1) + pl) * 2));
-            Si += st.x;
-            Qi += st.y;
-          }
-          const double mean = double(Si) * inv_sum;
-          double var = double(Qi) * inv_sq - mean * mean;
-          var = var > 0.0 ? var : 0.0;
-          const float rstd = rsqrtf(float(var) + L.gn_eps);
-          const float sc = ga[j] * rstd;
-          const float sh = be[j] - float(mean) * sc;
-          if constexpr (kFast && Cvt<T>::kFmt == 0) {  // half-scaled so that swish(y) = h*tanh(h) + h with h = y/2
-            table_h[c] = __float2half_rn(0.5f * sc);
-            table_h[kMaxGnC + c] = __float2half_rn(0.5f * sh);
-          } else if constexpr (kFast) {  // bf16 storage: fp32 affine, then the packed-half tanh form
-            table[c] = make_float2(0.5f * sc, 0.5f * sh);
-          } else {
-            table[c] = make_float2(sc, sh);
-          }
-        }
-      }
-      named_bar_sync(1, kProdThreads);
-    };
-    if (L.a_tma != 0) {
-      // ----------------------------------------------------------------- TMA-fed layers: the loader warp's
-      // tensor loads land the raw 128B-swizzled patch in the stage (out-of-image positions zero);
-      // these warps apply GroupNorm + Swish in place and hand the stage to the MMA warp.  The thread
-      // owns 16-byte slot (pidx & 7) of positions (pidx >> 3) + 40 i: byte pidx*16 + i*5120 of the stage
-      // (conflict-free: a warp covers 512 contiguous bytes).  40 positions are 5 swizzle periods, so the
-      // slot's logical channel group depends only on the stage
-      // (stage s starts 341 s = 5 s mod 8 rows into the swizzle period)
-      const int pos0 = pidx >> 3;
-      const int py0 = pos0 / kPatchW, px0 = pos0 - py0 * kPatchW;  // position of unit i: (py0 + 4 i, px0)
-      uint32_t smask = 0u;  // unit i = position pos0 + 40 i exists in the (TH + 2) x 10 patch
-#pragma unroll
-      for (int i = 0; i < kMaxUnits; ++i) smask |= (pos0 + 40 * i < npos) ? (1u << i) : 0u;
-      uint32_t rph = 0u;  // bit s: parity of the next phase of raw_full(s) (only GroupNorm chunks use it)
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        if (L.gn_C > 0 && b != cur_b) {
-          cur_b = b;
-          build_table(b);
-          if (pidx == 0 && tile == tile_begin) PROF_TS(2);  // GroupNorm table of the first image built
-        }
-        // units inside the image (padding must stay zero: swish(GN(0)) != 0)
-        const int y0 = ty * TH - 1 + py0, x0 = tx * kTileW - 1 + px0;
-        uint32_t vmask = 0u;
-        if (unsigned(x0) < unsigned(W)) {
-#pragma unroll
-          for (int i = 0; i < kMaxUnits; ++i) vmask |= unsigned(y0 + 4 * i) < unsigned(H) ? (1u << i) : 0u;
-          vmask &= smask;
-        }
-        PROF_MARK(0);
-        for (int c = 0; c < L.nchunks; ++c) {
-          const ConvChunk& ck = L.chunk[c];
-          if (ck.gn == 0) {  // raw chunk: the tensor load completes a_full by itself
-            if (ck.ring == 0 && ++as == nG) as = 0;
-            continue;
-          }
-          mbar_wait(bar_raw_full(as), (rph >> as) & 1u);
-          rph ^= 1u << as;
-          if (pidx == 0 && tile == tile_begin && c == 0) PROF_TS(3);  // first patch landed
-          PROF_MARK(1);
-          if (!(L.dbg & 2)) {
-            const int cgs = (pidx & 7) ^ ((pos0 + 5 * as) & 7);
-            float sc[8], sh[8];
-            uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
-            if constexpr (kFast && Cvt<T>::kFmt == 0) {
-              hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cgs * 8);
-              hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cgs * 8);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 e = table[ck.vc0 + cgs * 8 + j];
-                sc[j] = e.x;
-                sh[j] = e.y;
-              }
-            }
-            const uint32_t a0 = sA + as * kAStageBytes + uint32_t(pidx) * 16;  // (GroupNorm chunks: ring 0)
-            uint4 rv[kMaxUnits];
-#pragma unroll
-            for (int i = 0; i < kMaxUnits; ++i)
-              if ((vmask >> i) & 1u) rv[i] = lds128(a0 + i * (40 * 128));
-            if (ck.gn == 1) {
-#pragma unroll
-              for (int i = 0; i < kMaxUnits; ++i)
-                if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_swish_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
-            } else {  // GroupNorm without activation
-#pragma unroll
-              for (int i = 0; i < kMaxUnits; ++i)
-                if ((vmask >> i) & 1u) sts128(a0 + i * (40 * 128), gn_affine_unit<T, kFast>(rv[i], hsc, hsh, sc, sh));
-            }
-            fence_proxy_async_smem();
-          }
-          PROF_MARK(3);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a_full(as));
-          if (++as == nG) as = 0;
-        }
-        if ((tx += kTStep) >= tiles_x) {
-          tx -= tiles_x;
-          if (++ty == L.tiles_y) { ty = 0; ++b; }
-        }
-      }
-    } else {
-      // ----------------------------------------------------------------- gathered layers (nearest-upsample,
-      // space-to-depth, the 16-channel stem): predicated 16-byte global loads into registers,
-      // GroupNorm + Swish, 16-byte stores into the no-swizzle [channel group][position][8 ch] patch
-      const int lg = ncg == 8 ? 3 : (ncg == 4 ? 2 : (ncg == 2 ? 1 : 0));
-      const int cg = pidx & (ncg - 1);
-      const int nunits = kPatchPos * ncg;
-      // per-thread patch coordinates of the (up to) 9 16-byte units it fills: fixed for the launch
-      uint32_t pcoord[kMaxUnits];  // py | px << 8
-      uint32_t emask = 0u, smask = 0u;  // bit i: unit i carries data / unit i has a smem slot to fill
-      uint32_t cenmask = 0u;            // bit i: unit i lies in the 32x8 centre of the patch (no halo)
-#pragma unroll
-      for (int i = 0; i < kMaxUnits; ++i) {
-        const int u = pidx + i * kProdThreads;
-        const int pos = u >> lg;
-        const int py = pos / kPatchW, px = pos - py * kPatchW;
-        bool ex = u < nunits;
-        smask |= ex ? (1u << i) : 0u;
-        if (mode == kModeS2D && (py > kTileH || px > kTileW)) ex = false;  // 33x9 block patch
-        emask |= ex ? (1u << i) : 0u;
-        cenmask |= (py >= 1 && py <= kTileH && px >= 1 && px <= kTileW) ? (1u << i) : 0u;
-        pcoord[i] = uint32_t(py) | (uint32_t(px) << 8);
-      }
-      const int shl = mode == kModeS2D ? 1 : 0, shr = mode == kModeUp2x ? 1 : 0;
-      const int src_w = mode == kModeS2D ? 2 * W : (mode == kModeUp2x ? (W >> 1) : W);
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
-        if (L.gn_C > 0 && b != cur_b) {
-          cur_b = b;
-          build_table(b);
-        }
-        // ---- source pixel offsets of this thread's patch positions; vmask bit i = inside the image
-        int pixoff[kMaxUnits];
-        uint32_t vmask = 0u;
-#pragma unroll
-        for (int i = 0; i < kMaxUnits; ++i) {
-          const int y = y0 + int(pcoord[i] & 0xffu), x = x0 + int((pcoord[i] >> 8) & 0xffu);
-          const bool ok = ((emask >> i) & 1u) != 0u && unsigned(y) < unsigned(H) && unsigned(x) < unsigned(W);
-          const int off = ((y << shl) >> shr) * src_w + ((x << shl) >> shr);
-          pixoff[i] = ok ? off : 0;
-          vmask |= ok ? (1u << i) : 0u;
-        }
-        PROF_MARK(0);
-        for (int c = 0; c < L.nchunks; ++c) {
-          if (L.dbg & 2) {  // experiment: producers only hand over (stale) stages
-            mbar_wait(bar_a_empty(as), aph ^ 1);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a_full(as));
-            if (++as == kAStages) { as = 0; aph ^= 1; }
-            continue;
-          }
-          const ConvChunk& ck = L.chunk[c];
-          const ConvSrc& s = L.src[ck.src];
-          const int sC = s.C;
-          const uint32_t tmask = ck.gn != 0 ? vmask : 0u;  // units that get GroupNorm + Swish
-          // a chunk whose only tap is the centre one (one space-to-depth plane) never reads the halo:
-          // neither load nor store it
-          const uint32_t cm = (ck.ntaps == 1 && ck.tap_pos[0] == kPatchW + 1) ? cenmask : 0xffffffffu;
-          const uint32_t lmask = vmask & cm, stmask = smask & cm;
-          const bool gn = ck.gn != 0;
-          const uint8_t* base = reinterpret_cast<const uint8_t*>(
-              reinterpret_cast<const T*>(s.ptr) + (size_t(b) * s.H * s.W + ck.pix_delta) * sC + ck.c0 + cg * 8);
-          const uint32_t pix_bytes = uint32_t(sC) * 2u;
-          uint4 rv[kMaxUnits];
-#pragma unroll
-          for (int i = 0; i < kMaxUnits; ++i)
-            rv[i] = ldg16_pred(base + uint32_t(pixoff[i]) * pix_bytes, ((lmask >> i) & 1u) != 0u);
-          float sc[8], sh[8];
-          uint4 hsc = make_uint4(0u, 0u, 0u, 0u), hsh = hsc;
-          if (gn) {
-            if constexpr (kFast && Cvt<T>::kFmt == 0) {
-              hsc = *reinterpret_cast<const uint4*>(table_h + ck.vc0 + cg * 8);
-              hsh = *reinterpret_cast<const uint4*>(table_h + kMaxGnC + ck.vc0 + cg * 8);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 e = table[ck.vc0 + cg * 8 + j];
-                sc[j] = e.x;
-                sh[j] = e.y;
-              }
-            }
-          }
-          PROF_MARK(1);
-          mbar_wait(bar_a_empty(as), aph ^ 1);
-          PROF_MARK(2);
-          const uint32_t dst0 = sA + as * kAStageBytes + cg * kPlaneBytes + uint32_t(pidx >> lg) * 16;
-#pragma unroll
-          for (int i = 0; i < kMaxUnits; ++i) {
-            if ((stmask >> i) & 1u) {
-              uint4 o = rv[i];
-              if ((tmask >> i) & 1u)
-                o = ck.gn == 1 ? gn_swish_unit<T, kFast>(o, hsc, hsh, sc, sh) : gn_affine_unit<T, kFast>(o, hsc, hsh, sc, sh);
-              sts128(dst0 + uint32_t((i * kProdThreads) >> lg) * 16, o);
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a_full(as));
-          PROF_MARK(3);
-          if (++as == kAStages) { as = 0; aph ^= 1; }
-        }
-        if ((tx += kTStep) >= tiles_x) {
-          tx -= tiles_x;
-          if (++ty == L.tiles_y) { ty = 0; ++b; }
-        }
-      }
-    }
-    if (pidx == 0) PROF_FLUSH(2);
   }
 
   tc_fence_before();

@@ -271,13 +271,24 @@ class Engine:
                  float(self.lib.fdsr_debug_op_flops(self._h, i))) for i in range(n)]
 
     def role_cycles(self, op: int, t: int = 0):
-        """(n_cta, 4 roles, 8 slots) cycle counters of conv op `op` (FDSR_PROFILE builds only)."""
-        n = 148 * 32 * 2
+        """(n_cta, 5 roles, 8 slots) cycle counters of conv op `op` (FDSR_PROFILE builds only)."""
+        n = 148 * 40 * 2
         buf = (C.c_int64 * n)()
         with torch.cuda.device(self.device):
             m = self._check(self.lib.fdsr_debug_role_cycles(self._h, op, t, buf, n, self._stream()),
                             "fdsr_debug_role_cycles")
-        return np.array(buf[:m], dtype=np.int64).reshape(-1, 4, 8)
+        return np.array(buf[:m], dtype=np.int64).reshape(-1, 5, 8)
+
+    def timeline(self, t: int = 0, reps: int = 3):
+        """(n_ops, n_sms, 5 roles, 8 slots): the same counters of every conv op inside a running UNet evaluation
+        (FDSR_PROFILE builds only; tools/timeline.py)."""
+        nops = int(self.lib.fdsr_debug_num_ops(self._h))
+        nsm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        out = np.zeros((nops, nsm, 5, 8), dtype=np.int64)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.fdsr_debug_timeline(self._h, t, reps, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size,
+                                                     self._stream()), "fdsr_debug_timeline")
+        return out
 
     def launch_count(self):
         return int(self.lib.fdsr_launch_count(self._h))

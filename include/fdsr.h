@@ -197,9 +197,17 @@ double fdsr_debug_op_flops_executed(const fdsr_ctx* ctx, int32_t i);
 int fdsr_debug_profile_unet(fdsr_ctx* ctx, int32_t t, int32_t reps, float* ms_out_host, int32_t cap,
                             void* stream);
 /* Role-level cycle counters of one conv op (only populated by -DFDSR_PROFILE builds of the library,
- * used by tools/role_profile.py): out_host[(cta*4 + role)*8 + slot], role 0 = MMA issuer, 1 = epilogue,
- * 2 = producer.  Re-runs op `op` on the current buffers; returns the number of entries.  Synchronous. */
+ * used by tools/role_profile.py): out_host[(cta*5 + role)*8 + slot], role 0 = MMA issuer, 1 = epilogue,
+ * 2 = producer, 3 = timeline (cycles since kernel entry of: prologue done, previous launch complete, GroupNorm table
+ * built, first patch landed, first MMA, last MMA issued, epilogue done, exit), 4 = anchor {SM id, the SM's clock at
+ * kernel entry, %globaltimer at entry}.  Re-runs op `op` on the current buffers; returns the number of entries.
+ * Synchronous. */
 int fdsr_debug_role_cycles(fdsr_ctx* ctx, int32_t op, int32_t t, int64_t* out_host, int32_t cap, void* stream);
+/* The same counters of EVERY conv op inside a running UNet evaluation (tools/timeline.py): `reps` evaluations back to
+ * back, launched as the sampler launches them (programmatic dependent launch); out_host[op][sm][role][slot] of the
+ * last one (cap >= num_ops * num_sms * 40 entries).  Consecutive launches on one SM share its clock, so
+ * first-MMA(op k+1) - last-MMA(op k) is the tensor pipe's idle time between two layers.  Returns the number of ops. */
+int fdsr_debug_timeline(fdsr_ctx* ctx, int32_t t, int32_t reps, int64_t* out_host, int64_t cap, void* stream);
 /* Fills out_dev (B,3,H,W) with the N(0,1) values the built-in generator hands the sampler for step stream
  * `stream_id` (T for x_T, t for the z of step t) of images first_image .. first_image+B-1 under `seed`: lets tests
  * check the distribution (moments, Kolmogorov-Smirnov) and reproduce a built-in-noise sample through the

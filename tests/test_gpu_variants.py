@@ -16,6 +16,10 @@ form and the fp32 reference).
   FDSR_HALF_TILES=0  32 x 8 tiles everywhere (split-N / single accumulator at <= 64^2)  vs  16 x 8 half tiles as CTA pairs
   FDSR_EPI2=0        one epilogue team for every layer                               vs  producer warps 12..19 as a second
                      epilogue team (odd 32-column blocks) in the layers that have no producer work
+  FDSR_TAIL_HELP=0   the last tile of every CTA drained by warps 4..11 alone        vs  producer warps 12..19 joining as a
+                     second team for that one tile (its epilogue is exposed: nothing left to overlap it with)
+  FDSR_PATCH_FIRST=0 weight stages requested before the launch dependency resolves, the first patch after  vs  the first
+                     patch first (it heads the longer chain: patch -> GroupNorm pass -> first MMA)
   FDSR_STEM_TMA=0    16-channel stem input gathered by the producer warps           vs  two 8-channel TMA plane loads
   FDSR_FUSED_TAIL=0  sampler: pack_input / final conv -> eps / posterior kernels    vs  the final conv's epilogue doing the
                      posterior update in registers and rewriting the next step's input (checked on the sampler)
@@ -62,7 +66,8 @@ def base(oracle, schedule, inputs):
 
 
 @pytest.mark.parametrize("switch,tol", [("FDSR_S2D_TMA", 0.0), ("FDSR_SPLIT_N", 0.0), ("FDSR_STEM_TMA", 0.0),
-                                        ("FDSR_HALF_TILES", 0.0), ("FDSR_EPI2", 0.0), ("FDSR_PAIR", 3e-3), ("FDSR_RESID_MMA", 3e-3),
+                                        ("FDSR_HALF_TILES", 0.0), ("FDSR_EPI2", 0.0), ("FDSR_TAIL_HELP", 0.0), ("FDSR_PATCH_FIRST", 0.0),
+                                        ("FDSR_PAIR", 3e-3), ("FDSR_RESID_MMA", 3e-3),
                                         ("FDSR_UP_PHASES", 3e-3), ("FDSR_TMA_IN", 3e-3)])
 def test_alternative_paths_agree(oracle, schedule, inputs, base, switch, tol):
     eng0, eps0 = base
