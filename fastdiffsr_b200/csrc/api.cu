@@ -167,6 +167,7 @@ struct fdsr_ctx {
   bool epi2 = true;        // FDSR_EPI2=0: producer-free layers keep one epilogue team (warps 4..11)
   bool tail_help = true;   // FDSR_TAIL_HELP=0: the last tile of a CTA is drained by warps 4..11 alone
   bool patch_first = true; // FDSR_PATCH_FIRST=0: weight stages are requested before griddepcontrol.wait, the first patch after
+  bool defer_csync = true; // FDSR_DEFER_CSYNC=0: CTA pairs run a full cluster barrier in the prologue
   bool half_tiles = true;  // FDSR_HALF_TILES=0: 32 x 8 tiles everywhere (the <= 64^2 wide layers then use split-N / single accumulators)
   bool stem_tma = true;  // FDSR_STEM_TMA=0: the 16-channel stem input is gathered by the producer warps
   bool fused_tail = true;  // FDSR_FUSED_TAIL=0: the sampler runs pack_input / final conv -> eps / posterior as separate kernels
@@ -1231,6 +1232,7 @@ int upload_layers(fdsr_ctx* c) {
     }
     l.tail2 = (c->tail_help && !l.epi2 && k.out_mode == kOutAct && l.N >= 64) ? 1 : 0;
     l.patch_first = c->patch_first ? 1 : 0;
+    l.defer_csync = c->defer_csync ? 1 : 0;
     l.prof = c->d_prof;
     l.flags = reinterpret_cast<unsigned int*>(c->d_ws + kOffFlags);
     {
@@ -1621,6 +1623,8 @@ int fdsr_create(const fdsr_config* cfg, fdsr_ctx** out) {
     c->tail_help = !(e17 && e17[0] == '0');
     const char* e18 = getenv("FDSR_PATCH_FIRST");
     c->patch_first = !(e18 && e18[0] == '0');
+    const char* e19 = getenv("FDSR_DEFER_CSYNC");
+    c->defer_csync = !(e19 && e19[0] == '0');
     const char* e15 = getenv("FDSR_HALF_TILES");
     c->half_tiles = !(e15 && e15[0] == '0');
     const char* e13 = getenv("FDSR_STEM_TMA");

@@ -145,6 +145,7 @@ struct ConvLayer {
   int32_t tail2;           // 1: producer warps 12..19 join the epilogue of the CTA's LAST tile as a second team (layers with
                            //    producer work; the last tile's epilogue is exposed — nothing is left to overlap it with)
   int32_t patch_first;     // 1: the loader requests the CTA's first input patch before its first weight stages
+  int32_t defer_csync;     // 1 (pairs): the opening cluster barrier is split — arrive in the prologue, wait where needed
   int32_t tile_h;          // output rows per CTA tile: 32 (two 128-row MMA tiles) or 16 (one: "half tiles", see upload_layers)
   int32_t tiles_x, tiles_y, ntiles;
   int32_t group;           // tiles per assignment group (divides tiles_x * tiles_y)
@@ -155,7 +156,7 @@ struct ConvLayer {
   const SampleArgs* args;
   unsigned int* flags;     // context status word: bit 0 = an fp16 activation store saturated (overflow)
   int32_t dbg;             // experiments (tools/): bit0 skip epilogue work, bit1 skip producer work
-  long long* prof;         // role cycle counters [grid][4 roles][8 slots] (FDSR_PROFILE builds only)
+  long long* prof;         // role cycle counters [grid][5 roles][8 slots] (FDSR_PROFILE builds only)
 };
 
 }  // namespace fdsr

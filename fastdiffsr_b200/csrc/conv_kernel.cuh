@@ -385,6 +385,16 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   constexpr int NB = kPair ? N / 2 : N;                    // weight columns this CTA stages
   constexpr int kTStep = kPair ? 2 : 1;                    // a CTA of a pair walks every second tile
 
+  // The tensor maps are constants of the launch: fetch them now, so that the first patch load after the launch
+  // dependency resolves (and the first tile's stores) do not start with a descriptor miss.
+  if (warp == 1) {
+    if (lane < kMaxSrc && L.src[lane].ptr != nullptr && L.a_tma != 0) {
+      prefetch_tensormap(&L.in_map[lane]);
+      if (L.a_tma == 1) prefetch_tensormap(&L.in_map_c[lane]);
+    }
+    if (lane == 8 && L.out_mode == kOutAct && L.use_tma_store != 0) prefetch_tensormap(&L.out_map);
+    if (lane >= 9 && lane < 12 && L.phases > 1) prefetch_tensormap(&L.out_map_ph[lane - 9]);
+  }
   if (tid == 0) {
     for (int s = 0; s < kASlots; ++s) {
       mbar_init(bar_a_full(s), kProdWarps);
@@ -407,9 +417,18 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   if (warp == 0) tmem_alloc<Cfg::kTmemCols, kPair>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
-  if (kPair) cluster_sync_all();  // both CTAs' barriers and TMEM exist before any remote arrive / pair MMA
+  // both CTAs' barriers and TMEM exist before any remote arrive / pair MMA.  Only the two MMA warps ever touch the other
+  // CTA (relay arrives, cta_group::2 MMAs and commits): with L.defer_csync every thread just ARRIVES here, the MMA warps
+  // wait before their loop and everyone else before the closing cluster barrier — the loader and the producers of a CTA
+  // start earlier (tools/timeline.py: entry -> prologue done 1.4 us as a pair, 0.6 us alone)
+  const bool defer_cs = kPair && L.defer_csync != 0;
+  if (kPair) {
+    if (defer_cs) cluster_arrive();
+    else cluster_sync_all();
+  }
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (kPair && warp == 0 && defer_cs) cluster_wait();
   if (kPair && tid == 0) {
     // the pair MMA writes the same TMEM address in both CTAs: the two allocations must agree (they do: one CTA per
     // SM, one allocation per CTA); a mismatch would corrupt results silently, so fail loudly instead
@@ -783,7 +802,12 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
     }
     const double inv_sum = L.gn_inv_sum, inv_sq = L.gn_inv_sq;  // 1 / (fixed-point scale * elements per group), host-side
     bool table_valid = false;
+#ifdef FDSR_PROFILE
+    uint4 probe_ = make_uint4(0u, 0u, 0u, 0u);  // (timeline only) one plain 16-byte load of the first patch's first pixel
+#endif
     auto build_table = [&](int bb) {
+      const bool first_table = !table_valid;
+      (void)first_table;
       if (table_valid) named_bar_sync(1, kProdThreads);  // everyone is done reading the previous table
       table_valid = true;
 #pragma unroll
@@ -802,6 +826,16 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
             Si += st.x;
             Qi += st.y;
           }
+#ifdef FDSR_PROFILE
+          if (pidx == 0 && j == 0 && first_table) {
+            long long z_;
+            asm volatile("and.b64 %0, %1, 0;" : "=l"(z_) : "l"(Si + Qi));  // (the statistics have arrived)
+            if (z_ == 0) PROF_TS4(5);
+            unsigned z2_;
+            asm volatile("and.b32 %0, %1, 0;" : "=r"(z2_) : "r"(probe_.x ^ probe_.w));  // (... and the probe load)
+            if (z2_ == 0) PROF_TS4(7);
+          }
+#endif
           const double mean = double(Si) * inv_sum;
           double var = double(Qi) * inv_sq - mean * mean;
           var = var > 0.0 ? var : 0.0;
@@ -818,10 +852,20 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
           }
         }
       }
+      if (pidx == 0 && first_table) PROF_TS4(6);  // table entries of this thread written
       named_bar_sync(1, kProdThreads);
     };
     // (a dry run of build_table on stale statistics before the wait, to warm its code path, measured 0.4 % slower)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (pidx == 0) PROF_TS4(4);  // (producers) previous launch complete
+#ifdef FDSR_PROFILE
+    if (pidx == 0 && L.a_tma == 1 && L.gn_C > 0 && L.phases == 1 && tile_end > tile_begin) {
+      const ConvSrc& s0 = L.src[L.chunk[0].src];
+      const int yy = ty * TH - 1 < 0 ? 0 : ty * TH - 1, xx = tx * kTileW - 1 < 0 ? 0 : tx * kTileW - 1;
+      probe_ = ldg16_pred(reinterpret_cast<const uint8_t*>(s0.ptr) +
+                              ((size_t(b) * s0.H + yy) * s0.W + xx) * size_t(s0.C) * 2 + size_t(L.chunk[0].c0) * 2, true);
+    }
+#endif
     if (L.a_tma != 0) {
       // ----------------------------------------------------------------- TMA-fed layers: the loader warp's
       // tensor loads land the raw 128B-swizzled patch in the stage (out-of-image positions zero);
@@ -837,11 +881,6 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
       for (int i = 0; i < kMaxUnits; ++i) smask |= (pos0 + 40 * i < npos) ? (1u << i) : 0u;
       uint32_t rph = 0u;  // bit s: parity of the next phase of raw_full(s) (only GroupNorm chunks use it)
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        if (L.gn_C > 0 && b != cur_b) {
-          cur_b = b;
-          build_table(b);
-          if (pidx == 0 && tile == tile_begin) PROF_TS(2);  // GroupNorm table of the first image built
-        }
         // units inside the image (padding must stay zero: swish(GN(0)) != 0)
         const int y0 = ty * TH - 1 + py0, x0 = tx * kTileW - 1 + px0;
         uint32_t vmask = 0u;
@@ -849,6 +888,15 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
 #pragma unroll
           for (int i = 0; i < kMaxUnits; ++i) vmask |= unsigned(y0 + 4 * i) < unsigned(H) ? (1u << i) : 0u;
           vmask &= smask;
+        }
+        // (Tried and dropped — the first data of a launch arrives ~3 us after its dependency resolves, whatever asks for
+        //  it: gathering the CTA's first patch with plain loads from these threads, holding the weight requests back until
+        //  the first patch has landed, prefetching the tensor maps: none was faster; profiles/r2/ab_first_ldg.log,
+        //  ab_hold.log, ab_tensormap_prefetch.log.  A plain 16-byte load issued at the dependency returns after 1.3 us.)
+        if (L.gn_C > 0 && b != cur_b) {
+          cur_b = b;
+          build_table(b);
+          if (pidx == 0 && tile == tile_begin) PROF_TS(2);  // GroupNorm table of the first image built
         }
         PROF_MARK(0);
         for (int c = 0; c < L.nchunks; ++c) {
@@ -1391,6 +1439,7 @@ conv_gemm_kernel(const __grid_constant__ ConvLayer L, int t_step) {
   }
 
   tc_fence_before();
+  if (kPair && defer_cs && warp != 0) cluster_wait();  // (the opening barrier's wait, see above)
   __syncthreads();
   if (kPair) cluster_sync_all();  // neither CTA frees its TMEM / exits while the pair's MMAs or commits may still touch it
   if (tid == 0) PROF_TS(7);

@@ -75,6 +75,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 
 // 4-D bulk tensor load global -> shared through a TMA descriptor (coordinates innermost first; may be
 // negative / past the end: out-of-bounds elements are zero-filled and still counted in complete_tx)
+// bring a tensor map into the descriptor cache ahead of its first use (the map may live in kernel parameter space)
+__device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(const void* tmap, uint32_t dst_smem, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
   asm volatile(
@@ -118,6 +122,9 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
+// split form: every thread arrives once and waits once per phase; the wait may come much later (and un-converged)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

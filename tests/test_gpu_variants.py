@@ -20,6 +20,7 @@ form and the fp32 reference).
                      second team for that one tile (its epilogue is exposed: nothing left to overlap it with)
   FDSR_PATCH_FIRST=0 weight stages requested before the launch dependency resolves, the first patch after  vs  the first
                      patch first (it heads the longer chain: patch -> GroupNorm pass -> first MMA)
+  FDSR_DEFER_CSYNC=0 CTA pairs: full cluster barrier in the prologue               vs  arrive there, wait where needed
   FDSR_STEM_TMA=0    16-channel stem input gathered by the producer warps           vs  two 8-channel TMA plane loads
   FDSR_FUSED_TAIL=0  sampler: pack_input / final conv -> eps / posterior kernels    vs  the final conv's epilogue doing the
                      posterior update in registers and rewriting the next step's input (checked on the sampler)
@@ -66,7 +67,7 @@ def base(oracle, schedule, inputs):
 
 
 @pytest.mark.parametrize("switch,tol", [("FDSR_S2D_TMA", 0.0), ("FDSR_SPLIT_N", 0.0), ("FDSR_STEM_TMA", 0.0),
-                                        ("FDSR_HALF_TILES", 0.0), ("FDSR_EPI2", 0.0), ("FDSR_TAIL_HELP", 0.0), ("FDSR_PATCH_FIRST", 0.0),
+                                        ("FDSR_HALF_TILES", 0.0), ("FDSR_EPI2", 0.0), ("FDSR_TAIL_HELP", 0.0), ("FDSR_PATCH_FIRST", 0.0), ("FDSR_DEFER_CSYNC", 0.0),
                                         ("FDSR_PAIR", 3e-3), ("FDSR_RESID_MMA", 3e-3),
                                         ("FDSR_UP_PHASES", 3e-3), ("FDSR_TMA_IN", 3e-3)])
 def test_alternative_paths_agree(oracle, schedule, inputs, base, switch, tol):

@@ -97,6 +97,19 @@ for a, b in zip(conv_ops[:-1], conv_ops[1:]):
     tot_idle += idle
     tot_busy += us(np.median(busy))
     rows.append(med)
+# inside dep -> table (producer thread 0 of every CTA): launch dependency seen -> statistics arrived -> entries written -> barrier
+pd = []
+for op in conv_ops:
+    c = tl[op]
+    ok = (c[:, 4, 4] > 0) & (c[:, 4, 5] > 0) & (c[:, 4, 6] > 0) & (c[:, 3, 2] > 0)
+    if ok.any():
+        pd.append(np.median(np.stack([c[ok, 4, 5] - c[ok, 4, 4], c[ok, 4, 6] - c[ok, 4, 5], c[ok, 3, 2] - c[ok, 4, 6],
+                                      c[ok, 4, 4] - c[ok, 3, 1], c[ok, 4, 7] - c[ok, 4, 4]], 1), axis=0))
+if pd:
+    m4 = np.median(np.array(pd), axis=0)
+    print(f"GroupNorm table (median over layers): dependency seen by the producers {us(m4[3]):+.2f} us after warp 0, "
+          f"statistics arrived +{us(m4[0]):.2f}, entries written +{us(m4[1]):.2f}, barrier passed +{us(m4[2]):.2f} us; "
+          f"a plain 16-byte load of the patch's first pixel issued at the dependency had arrived by +{us(m4[4]):.2f} us")
 print(f"sum over {len(rows)} layer boundaries: tensor pipe idle {tot_idle:.1f} us, issuing {tot_busy:.1f} us "
       f"({100 * tot_idle / (tot_idle + tot_busy):.1f} % of the evaluation idle between layers)")
 m = np.median(np.array(rows), axis=0)
