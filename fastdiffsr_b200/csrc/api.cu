@@ -2268,12 +2268,14 @@ int fdsr_debug_timeline(fdsr_ctx* c, int32_t t, int32_t reps, int64_t* out_host,
   CUDA_TRY(c, cudaMalloc(&buf, n * 8));
   for (size_t i = 0; i < c->ops.size(); ++i)
     if (c->ops[i].kind == 0) c->h_layers[c->ops[i].idx].prof = buf + i * per_op;
-  for (int r = 0; r < reps && rc == FDSR_OK; ++r) {
-    if (r + 1 == reps) cudaMemsetAsync(buf, 0, n * 8, st);
-    rc = unet_dispatch(c, t, st, false);
+  cudaError_t e = cudaSuccess;
+  for (int r = 0; r < reps && rc == FDSR_OK && e == cudaSuccess; ++r) {
+    if (r + 1 == reps) e = cudaMemsetAsync(buf, 0, n * 8, st);
+    if (e == cudaSuccess) rc = unet_dispatch(c, t, st, false);
   }
-  cudaError_t e = cudaMemcpyAsync(out_host, buf, n * 8, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (rc == FDSR_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_host, buf, n * 8, cudaMemcpyDeviceToHost, st);
+  const cudaError_t e_sync = cudaStreamSynchronize(st);  // (also on failure: nothing may still write into buf when it is freed)
+  if (e == cudaSuccess) e = e_sync;
   for (size_t i = 0; i < c->ops.size(); ++i)
     if (c->ops[i].kind == 0) c->h_layers[c->ops[i].idx].prof = c->d_prof;
   cudaFree(buf);
