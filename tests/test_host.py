@@ -240,3 +240,20 @@ def test_reference_DDPM_wrapper_runs_on_patched_define_G(oracle, tmp_path):
         sys.path[:] = saved_path
         for name in set(sys.modules) - saved_mods:
             del sys.modules[name]
+
+
+def test_documented_results_match_the_committed_records(tmp_path):
+    """Measurement hygiene: the result tables of README.md / DESIGN.md are generated from the bench
+    records under profiles/r2, and traffic.json (what bench.py's roofline.traffic quotes) from the raw ncu pages —
+    a hand-edited number or a stale table fails here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "tools/fill_tables.py", "--check"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = tmp_path / "traffic.json"
+    r = subprocess.run([sys.executable, "tools/extract_traffic.py", "profiles/r2", str(out)], cwd=root, capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.load(open(out))["launches"] == json.load(open(os.path.join(root, "profiles", "r2", "traffic.json")))["launches"]

@@ -1,6 +1,6 @@
 """profiles/<tag>/traffic.json from the raw pages of the full-set ncu captures (tools/make_profiles.sh writes conv<idx>_raw.csv):
 DRAM bytes, tensor-pipe activity and shared-memory wavefronts per captured launch — what bench.py's roofline.traffic quotes.
-python tools/extract_traffic.py profiles/r2"""
+python tools/extract_traffic.py profiles/r2 [output.json, default profiles/r2/traffic.json]"""
 import csv
 import json
 import os
@@ -41,7 +41,7 @@ for idx, name in LAUNCHES.items():
             except ValueError:
                 rec[k] = {"value": vals[i], "unit": units[i]}
     out["launches"][name] = rec
-json.dump(out, open(os.path.join(d, "traffic.json"), "w"), indent=1)
+json.dump(out, open(sys.argv[2] if len(sys.argv) > 2 else os.path.join(d, "traffic.json"), "w"), indent=1)
 for name, rec in out["launches"].items():
     rd, wr = rec.get("dram__bytes_read.sum", {}), rec.get("dram__bytes_write.sum", {})
     print(f"{name}: {rec.get('gpu__time_duration.sum', {}).get('value')} us, DRAM read {rd.get('value')} {rd.get('unit')}, "
